@@ -1,0 +1,459 @@
+"""Host-side mirror of the reference's Python module `ggnn` (src/ggnn/python/nanobind.cu:131-301) on top
+of the C ABI (include/ggnn_b200.h).  Same class / method names, arguments, defaults and return types:
+
+    my_ggnn = GGNN(); my_ggnn.set_base(base); my_ggnn.build(24, 0.5)
+    indices, dists = my_ggnn.query(query, 10, 0.64, 400)
+    gt, _ = my_ggnn.bf_query(query, 10)
+    Evaluator(base, query, gt, 10).evaluate_results(indices)
+
+torch is used for device memory, streams and peer copies only; every computation on the path is a
+kernel of libggnn_b200.so.  No CPU fallback: without a CUDA device the calls raise.
+"""
+import ctypes as C
+import math
+import os
+from enum import IntEnum
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class DistanceMeasure(IntEnum):  # include/ggnn/base/def.h:27-30
+    Euclidean = 0
+    Cosine = 1
+
+
+_log_level = 0
+
+
+def set_log_level(level):  # nanobind.cu:151
+    global _log_level
+    _log_level = int(level)
+
+
+def _log(level, *a):
+    if _log_level >= level:
+        print("[ggnn_b200]", *a, flush=True)
+
+
+def _as_tensor(x, what):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    if hasattr(x, "tensor"):  # FloatDataset & co
+        x = x.tensor
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{what} must be a torch tensor or numpy array")
+    if x.dim() != 2:
+        raise ValueError(f"{what} must be 2-dimensional [N, D]")
+    return x
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Graph:
+    """Read-only view of one shard's graph (nanobind.cu:295-300; layout src/ggnn/base/graph.cpp:33-92)."""
+
+    def __init__(self, cfg, blob):
+        self.config = cfg
+        self.blob = blob  # uint8 tensor on the device (or CPU)
+        o = _lib.graph_offsets(cfg)
+        K = cfg.KBuild
+        self.graph = blob[o.graph:o.graph + cfg.N_all * K * 4].view(torch.int32).view(cfg.N_all, K)
+        self.translation = blob[o.translation:o.translation + cfg.ST_all * 4].view(torch.int32)
+        self.selection = blob[o.selection:o.selection + cfg.ST_all * 4].view(torch.int32)
+        self.nn1_stats = blob[o.nn1_stats:o.nn1_stats + 8].view(torch.float32)
+
+    def layer_graph(self, l):
+        c = self.config
+        return self.graph[c.Ns_offsets[l]:c.Ns_offsets[l] + c.Ns[l]]
+
+    def layer_translation(self, l):
+        c = self.config
+        return self.translation[c.STs_offsets[l]:c.STs_offsets[l] + c.Ns[l]] if l else None
+
+    def layer_selection(self, l):
+        c = self.config
+        return self.selection[c.STs_offsets[l]:c.STs_offsets[l] + c.Ns[l]] if l else None
+
+
+class _Shard:
+    def __init__(self, device, base, global_id):
+        self.device = device
+        self.base = base          # [N_shard, D] fp32 on `device`
+        self.global_id = global_id
+        self.graph = None         # Graph
+
+
+class GGNN:
+    """Drop-in for ggnn.GGNN (include/ggnn/base/ggnn.cuh:41-182, nanobind.cu:184-267)."""
+
+    MIN_D, MAX_D = 1, 4096
+    MIN_KBUILD, MAX_KBUILD = 2, 512
+
+    def __init__(self):
+        self._base = None
+        self._gpus = [0]
+        self._shard_size = 0
+        self._workdir = "."
+        self._results_on_gpu = False
+        self._shards = []
+        self._kbuild = None
+        self._measure = None
+        self._work_counters = {}
+
+    # ---- configuration (ggnn.cu:53-60, 420-454) ----
+    def set_working_directory(self, path):
+        self._workdir = str(path)
+
+    def set_cpu_memory_limit(self, limit):
+        self._cpu_limit = int(limit)  # shards stay resident in HBM here (180 GB per GPU)
+
+    def set_reserved_gpu_memory(self, reserved):
+        self._reserved = int(reserved)
+
+    def set_gpus(self, gpu_ids):
+        if self._shards:
+            raise RuntimeError("GPUs cannot be changed after the graph has been set up")  # ggnn.cu:146-152
+        self._gpus = [int(g) for g in gpu_ids]
+        if not self._gpus:
+            raise ValueError("at least one GPU is required")
+
+    def set_shard_size(self, n_shard):
+        if self._shards:
+            raise RuntimeError("shard size cannot be changed after the graph has been set up")
+        self._shard_size = int(n_shard)
+
+    def set_return_results_on_gpu(self, flag=True):
+        self._results_on_gpu = bool(flag)
+
+    def set_base(self, base):
+        base = _as_tensor(base, "base")
+        if base.dtype != torch.float32:
+            raise NotImplementedError("only float32 base vectors are built (uint8 is a 'next' row)")
+        if self._shards:
+            raise RuntimeError("base cannot be changed after the graph has been set up")
+        if not (self.MIN_D <= base.shape[1] <= self.MAX_D):
+            raise ValueError("unsupported dimension")
+        self._base = base.contiguous()  # the reference copies its input as well (nanobind.cu:102-110)
+
+    # ---- sharding (ggnn.cu:154-203) ----
+    def _prepare(self, k_build):
+        if self._base is None:
+            raise RuntimeError("The base needs to be set before building a graph.")
+        if not torch.cuda.is_available():
+            raise RuntimeError("ggnn_b200 needs a CUDA device (there is no CPU fallback)")
+        if not (self.MIN_KBUILD <= k_build <= self.MAX_KBUILD):
+            raise ValueError("KBuild out of range")
+        if self._shards:
+            if self._kbuild != k_build:
+                raise RuntimeError("graph already set up with a different KBuild")
+            return
+        N = self._base.shape[0]
+        n_shard = self._shard_size or N
+        if N % n_shard:
+            raise ValueError("base size must be divisible by the shard size")
+        num_shards = N // n_shard
+        if num_shards % len(self._gpus):
+            raise ValueError("number of shards must be divisible by the number of GPUs")
+        self._spg = num_shards // len(self._gpus)
+        self._n_shard = n_shard
+        self._kbuild = k_build
+        for gi, gpu in enumerate(self._gpus):
+            dev = torch.device("cuda", gpu)
+            for s in range(self._spg):
+                gid = gi * self._spg + s
+                rows = self._base[gid * n_shard:(gid + 1) * n_shard]
+                self._shards.append(_Shard(dev, rows.to(dev, non_blocking=True).contiguous(), gid))
+        _lib.lib()  # fail early if the CUDA library is missing
+
+    def _cfg(self):
+        return _lib.graph_config(self._n_shard, self._base.shape[1], self._kbuild)
+
+    # ---- build / store / load ----
+    def build(self, k_build, tau_build, refinement_iterations=2, measure=DistanceMeasure.Euclidean):
+        self._prepare(int(k_build))
+        cfg = self._cfg()
+        l = _lib.lib()
+        blob_bytes = l.ggnn_b200_graph_blob_bytes(C.byref(cfg))
+        scratch_bytes = l.ggnn_b200_build_scratch_bytes(C.byref(cfg))
+        for sh in self._shards:
+            with torch.cuda.device(sh.device):
+                blob = torch.zeros(blob_bytes, dtype=torch.uint8, device=sh.device)
+                scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=sh.device)
+                _lib.check(l.ggnn_b200_build_graph(C.byref(cfg), _ptr(sh.base), int(measure), float(tau_build),
+                                                   int(refinement_iterations), None, _ptr(blob), _ptr(scratch),
+                                                   scratch_bytes, _stream_ptr(sh.device)))
+                sh.graph = Graph(cfg, blob)
+                torch.cuda.current_stream(sh.device).synchronize()
+                del scratch
+        self._measure = int(measure)
+
+    def store(self):
+        if not self._shards or self._shards[0].graph is None:
+            raise RuntimeError("There is no graph to store.")
+        os.makedirs(self._workdir, exist_ok=True)
+        for sh in self._shards:  # gpu_instance.cu:86-115: part_<global_shard_id>.ggnn = raw blob
+            sh.graph.blob.cpu().numpy().tofile(os.path.join(self._workdir, f"part_{sh.global_id}.ggnn"))
+
+    def load(self, k_build):
+        self._prepare(int(k_build))
+        cfg = self._cfg()
+        nbytes = _lib.lib().ggnn_b200_graph_blob_bytes(C.byref(cfg))
+        for sh in self._shards:
+            path = os.path.join(self._workdir, f"part_{sh.global_id}.ggnn")
+            if os.path.getsize(path) != nbytes:  # gpu_instance.cu:454-455 validates by size only
+                raise RuntimeError(f"{path}: unexpected file size")
+            blob = torch.from_numpy(np.fromfile(path, dtype=np.uint8)).to(sh.device)
+            sh.graph = Graph(cfg, blob)
+
+    def get_graph(self, global_shard_id=0):
+        return self._shards[global_shard_id].graph
+
+    # ---- query ----
+    def _counter(self, device):
+        if device not in self._work_counters:
+            self._work_counters[device] = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._work_counters[device]
+
+    def _query_device(self, gpu_index, q_dev, k_query, tau_query, max_iterations, measure):
+        """all shards of one GPU -> sorted [Nq, K] ids (GPU-local numbering) + dists on that GPU"""
+        l = _lib.lib()
+        shards = self._shards[gpu_index * self._spg:(gpu_index + 1) * self._spg]
+        dev = shards[0].device
+        Nq = q_dev.shape[0]
+        with torch.cuda.device(dev):
+            ids = torch.empty((Nq, k_query * self._spg), dtype=torch.int32, device=dev)
+            dists = torch.empty((Nq, k_query * self._spg), dtype=torch.float32, device=dev)
+            for s, sh in enumerate(shards):
+                cfg = sh.graph.config
+                p = _lib.QueryParams()
+                p.D, p.measure, p.KQuery = cfg.D, int(measure), int(k_query)
+                p.tau_query, p.max_iterations = float(tau_query), int(max_iterations)
+                p.N_base, p.KBuild, p.num_starting_points = cfg.N, cfg.KBuild, cfg.S
+                p.d_base, p.d_query = sh.base.data_ptr(), q_dev.data_ptr()
+                p.d_graph = sh.graph.graph.data_ptr()
+                p.d_starting_points = sh.graph.layer_translation(_lib.L - 1).data_ptr()
+                p.d_nn1_stats = sh.graph.nn1_stats.data_ptr()
+                p.d_query_results, p.d_query_results_dists = ids.data_ptr(), dists.data_ptr()
+                p.shards_per_gpu, p.on_gpu_shard_id = self._spg, s
+                p.d_work_counter = self._counter(dev).data_ptr()
+                _lib.check(l.ggnn_b200_query(C.byref(p), Nq, _stream_ptr(dev)))
+            if self._spg > 1:  # replaces the segmented sort gpu_instance.cu:745-790
+                out_i = torch.empty((Nq, k_query), dtype=torch.int32, device=dev)
+                out_d = torch.empty((Nq, k_query), dtype=torch.float32, device=dev)
+                _lib.check(l.ggnn_b200_merge_topk(_ptr(ids), _ptr(dists), self._spg, k_query, k_query * self._spg,
+                                                  k_query, Nq, k_query, 0, _ptr(out_i), _ptr(out_d), _stream_ptr(dev)))
+                ids, dists = out_i, out_d
+        return ids, dists
+
+    def query(self, query, k_query, tau_query, max_iterations=400, measure=DistanceMeasure.Euclidean):
+        if not self._shards or self._shards[0].graph is None:
+            raise RuntimeError("There is no graph to query.")
+        query = _as_tensor(query, "query")
+        if query.dtype != self._base.dtype:
+            raise ValueError("query data type has to match base data type")  # ggnn.cu:524-540
+        if query.shape[1] != self._base.shape[1]:
+            raise ValueError("query dimension does not match the base")
+        l = _lib.lib()
+        k_query = int(k_query)
+        n_gpus = len(self._gpus)
+        if self._results_on_gpu and n_gpus > 1:
+            raise RuntimeError("Returning query results on GPU is only possible when using a single GPU.")
+        per_gpu = []
+        for gi in range(n_gpus):
+            dev = self._shards[gi * self._spg].device
+            q_dev = query.to(dev, non_blocking=True).contiguous()
+            per_gpu.append(self._query_device(gi, q_dev, k_query, tau_query, max_iterations, measure))
+        dev0 = self._shards[0].device
+        if n_gpus == 1:
+            ids, dists = per_gpu[0]
+        else:  # replaces ResultMerger::merge (result_merger.cpp:51-149): peer copies + one merge kernel
+            with torch.cuda.device(dev0):
+                Nq = query.shape[0]
+                all_i = torch.empty((n_gpus, Nq, k_query), dtype=torch.int32, device=dev0)
+                all_d = torch.empty((n_gpus, Nq, k_query), dtype=torch.float32, device=dev0)
+                for gi, (i_, d_) in enumerate(per_gpu):
+                    torch.cuda.current_stream(i_.device).synchronize()
+                    all_i[gi].copy_(i_, non_blocking=True)
+                    all_d[gi].copy_(d_, non_blocking=True)
+                ids = torch.empty((Nq, k_query), dtype=torch.int32, device=dev0)
+                dists = torch.empty((Nq, k_query), dtype=torch.float32, device=dev0)
+                _lib.check(l.ggnn_b200_merge_topk(_ptr(all_i), _ptr(all_d), n_gpus, Nq * k_query, k_query, k_query, Nq,
+                                                  k_query, self._spg * self._n_shard, _ptr(ids), _ptr(dists),
+                                                  _stream_ptr(dev0)))
+        if self._results_on_gpu:
+            return ids, dists
+        return ids.cpu(), dists.cpu()
+
+    def bf_query(self, query, k_gt=100, measure=DistanceMeasure.Euclidean):
+        if self._base is None:
+            raise RuntimeError("The base needs to be set before running a brute-force query.")
+        if len(self._gpus) > 1:
+            raise RuntimeError("bf_query supports only a single GPU")  # ggnn.cu:338-339
+        if not torch.cuda.is_available():
+            raise RuntimeError("ggnn_b200 needs a CUDA device (there is no CPU fallback)")
+        query = _as_tensor(query, "query")
+        dev = torch.device("cuda", self._gpus[0])
+        l = _lib.lib()
+        with torch.cuda.device(dev):
+            if self._shards and len(self._shards) == 1:
+                base = self._shards[0].base
+            else:
+                base = self._base.to(dev).contiguous()
+            q = query.to(dev).contiguous()
+            Nq = q.shape[0]
+            ids = torch.empty((Nq, k_gt), dtype=torch.int32, device=dev)
+            dists = torch.empty((Nq, k_gt), dtype=torch.float32, device=dev)
+            p = _lib.BfQueryParams()
+            p.D, p.measure, p.KQuery, p.N_base = base.shape[1], int(measure), int(k_gt), base.shape[0]
+            p.d_base, p.d_query = base.data_ptr(), q.data_ptr()
+            p.d_query_results, p.d_query_results_dists = ids.data_ptr(), dists.data_ptr()
+            _lib.check(l.ggnn_b200_bf_query(C.byref(p), Nq, _stream_ptr(dev)))
+        if self._results_on_gpu:
+            return ids, dists
+        return ids.cpu(), dists.cpu()
+
+
+class Evaluation:  # include/ggnn/base/eval.h:39-48, nanobind.cu:280-293
+    def __init__(self, k_query, c1, c1_dup, c_k_query, c_k_query_dup, r_k_query, r_k_query_dup):
+        self.k_query, self.c1, self.c1_dup = k_query, c1, c1_dup
+        self.c_k_query, self.c_k_query_dup = c_k_query, c_k_query_dup
+        self.r_k_query, self.r_k_query_dup = r_k_query, r_k_query_dup
+
+    def __repr__(self):
+        return (f"c@1 (=r@1): {self.c1:.6g} +duplicates: {self.c1_dup:.6g}\n"
+                f"c@{self.k_query}: {self.c_k_query:.6g} +duplicates: {self.c_k_query_dup:.6g}\n"
+                f"r@{self.k_query}: {self.r_k_query:.6g} +duplicates: {self.r_k_query_dup:.6g}")
+
+
+class Evaluator:
+    """Recall metrics of the reference (src/ggnn/base/eval.cpp:88-242): c@1, c@K (= "recall@K"), r@K and
+    their duplicate-aware variants (ground-truth prefixes extended over distance ties <= 1e-6)."""
+
+    def __init__(self, base, query, gt, k_query, measure=DistanceMeasure.Euclidean):
+        self.k_query = int(k_query)
+        gt = _as_tensor(gt, "gt").cpu().to(torch.int64)
+        self.gt = gt
+        Nq, Kgt = gt.shape
+        self.end1 = self.endk = None
+        if base is None or query is None:
+            return
+        base = _as_tensor(base, "base").cpu().float()
+        query = _as_tensor(query, "query").cpu().float()
+        eps = 1e-6
+        # distances of every ground-truth entry to its query (eval.cpp:37-65)
+        g = base[gt.reshape(-1)].view(Nq, Kgt, -1)
+        q = query[:Nq].unsqueeze(1)
+        if int(measure) == 0:
+            d = ((g - q) ** 2).sum(-1).sqrt()
+        else:
+            a_norm = (g * g).sum(-1)
+            prod = a_norm * a_norm  # reference quirk: b_norm is computed from a (eval.cpp:52)
+            d = torch.where(prod > 0, (1.0 - (g * q).sum(-1) / prod.sqrt()).abs(), torch.ones_like(a_norm))
+        # eval.cpp:135-167: extend while dist_k - dist_ref <= eps (stops at the first larger one)
+        def run_len(ref_col, start):
+            ok = (d[:, start:] - d[:, ref_col:ref_col + 1]) <= eps
+            return torch.cumprod(ok.to(torch.int64), dim=1).sum(1)
+        self.end1 = 1 + run_len(0, 1)
+        if self.k_query <= Kgt:
+            self.endk = self.k_query + run_len(self.k_query - 1, self.k_query)
+        else:
+            self.endk = torch.full((Nq,), Kgt, dtype=torch.int64)
+
+    def evaluate_results(self, results):
+        res = _as_tensor(results, "results").cpu().to(torch.int64)
+        K = self.k_query
+        Nq = res.shape[0]
+        gt = self.gt[:Nq]
+        Kgt = gt.shape[1]
+        has_dup = self.end1 is not None
+        end1 = self.end1[:Nq] if has_dup else torch.ones(Nq, dtype=torch.int64)
+        endk = self.endk[:Nq] if has_dup else torch.full((Nq,), K, dtype=torch.int64)
+        eq = res[:, :K].unsqueeze(2) == gt.unsqueeze(1)            # [Nq, K(result), Kgt]
+        kg = torch.arange(Kgt).view(1, 1, Kgt)
+        within = kg < endk.view(-1, 1, 1)
+        eq = eq & within
+        c1 = (eq[:, 0, 0]).sum().item()
+        rK = (eq[:, :, 0]).sum().item() if K > 0 else 0
+        rK_dup = rK
+        c1_dup = (eq[:, 0, :] & (kg[0] < end1.view(-1, 1))).sum().item()
+        cK = (eq & (kg < K)).sum().item()
+        cK_dup = eq.sum().item()
+        inv_q, inv_r = 1.0 / Nq, 1.0 / (Nq * K)
+        nan = float("nan")
+        return Evaluation(K, c1 * inv_q, c1_dup * inv_q if has_dup else nan, cK * inv_r,
+                          cK_dup * inv_r if has_dup else nan, rK * inv_q, rK_dup * inv_q if has_dup else nan)
+
+
+class _Dataset:
+    """FloatDataset / UCharDataset / IntDataset of the reference (nanobind.cu:157-182): thin wrapper
+    around a 2-D tensor with fvecs/bvecs/ivecs IO (src/ggnn/base/dataset.cu:118-233)."""
+    dtype = torch.float32
+    np_dtype = np.float32
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+    @classmethod
+    def load(cls, file, from_=0, num=2 ** 32 - 1, pin_memory=False):
+        raw = np.fromfile(file, dtype=np.uint8)
+        d = int(raw[:4].view(np.int32)[0])
+        esz = np.dtype(cls.np_dtype).itemsize
+        rec = 4 + d * esz
+        n_total = raw.size // rec
+        lo, hi = min(from_, n_total), min(n_total, from_ + num)
+        body = raw[:n_total * rec].reshape(n_total, rec)[lo:hi, 4:]
+        t = torch.from_numpy(np.ascontiguousarray(body).view(cls.np_dtype).reshape(hi - lo, d).copy())
+        if pin_memory and torch.cuda.is_available():
+            t = t.pin_memory()
+        return cls(t)
+
+    def store(self, file):
+        t = self.tensor.cpu().numpy()
+        n, d = t.shape
+        out = np.empty((n, 4 + d * t.dtype.itemsize), dtype=np.uint8)
+        out[:, :4] = np.frombuffer(np.int32(d).tobytes(), dtype=np.uint8)
+        out[:, 4:] = t.view(np.uint8).reshape(n, -1)
+        out.tofile(file)
+
+    @property
+    def N(self):
+        return self.tensor.shape[0]
+
+    @property
+    def D(self):
+        return self.tensor.shape[1]
+
+    def numel(self):
+        return self.tensor.numel()
+
+    def clone(self):
+        return type(self)(self.tensor.clone())
+
+    @property
+    def view(self):
+        return self.tensor
+
+    @property
+    def device(self):
+        return self.tensor.device
+
+
+class FloatDataset(_Dataset):
+    dtype, np_dtype = torch.float32, np.float32
+
+
+class UCharDataset(_Dataset):
+    dtype, np_dtype = torch.uint8, np.uint8
+
+
+class IntDataset(_Dataset):
+    dtype, np_dtype = torch.int32, np.int32

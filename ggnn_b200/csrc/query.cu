@@ -1,0 +1,256 @@
+// query.cu -- batched ANN query: best-first traversal of the layer-0 kNN graph, one warp per query.
+// Replaces src/ggnn/query/query_layer.cu:39-97 + include/ggnn/cuda_utils/simple_knn_cache.cuh of the
+// reference; launcher replaces src/ggnn/query/query_kernels.cu:50-186.
+#include "traverse.cuh"
+#include "host_util.h"
+#include "../../include/ggnn_b200.h"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace g200 {
+
+struct QueryArgs {
+  ggnn_b200_query_params p;
+  uint32_t N_query;
+  uint32_t warps_per_cta;
+  uint32_t warp_smem_bytes;
+  uint32_t stage_rows;
+  uint32_t hsize;      // visited hash slots (power of two)
+  uint32_t ring_cap;   // 0 = ring mirror not needed
+  uint32_t off_sq, off_sorted, off_hash, off_ring, off_bar;  // byte offsets in the per-warp block
+};
+
+template <int NS, bool FAST, int NI>
+__global__ void __launch_bounds__(256, 2) query_kernel(const QueryArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const ggnn_b200_query_params& p = a.p;
+
+  unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * a.warp_smem_bytes;
+  WarpSmem ws;
+  ws.stage = reinterpret_cast<float*>(wbase);
+  ws.s_q = reinterpret_cast<float*>(wbase + a.off_sq);
+  ws.s_sorted = reinterpret_cast<int*>(wbase + a.off_sorted);
+  ws.bar = reinterpret_cast<uint64_t*>(wbase + a.off_bar);
+  ws.parity = 0;
+  ws.stage_rows = a.stage_rows;
+  if (lane == 0) mbar_init(ws.bar, 1);
+  mbar_fence_init();
+  __syncwarp();
+
+  VisitedSet V;
+  V.tab = reinterpret_cast<int*>(wbase + a.off_hash);
+  V.hmask = a.hsize - 1;
+  V.hshift = 32 - (31 - __clz(a.hsize));
+  V.ring = a.ring_cap ? reinterpret_cast<int*>(wbase + a.off_ring) : nullptr;
+  V.vcap = p.cache_size - p.sorted_size;
+  V.vpos = 0;
+
+  const DistCfg dc{p.D, p.block_dim_x, 4u, p.measure};
+  // query_layer.cu:48-50
+  const float max_nn1 = p.d_nn1_stats[1];
+  const float xi = (p.measure == 0) ? __fmul_rn(__fmul_rn(__fmul_rn(max_nn1, max_nn1), p.tau_query), p.tau_query)
+                                    : __fmul_rn(max_nn1, p.tau_query);
+
+  const uint32_t total_warps = gridDim.x * a.warps_per_cta;
+  uint32_t n = blockIdx.x * a.warps_per_cta + warp;
+  if (p.d_work_counter) {
+    if (lane == 0) n = atomicAdd(p.d_work_counter, 1u);
+    n = __shfl_sync(FULL, n, 0);
+  }
+
+  while (n < a.N_query) {
+    QueryVec<FAST, NI, 1> qv;
+    qv.load(dc, p.d_query + static_cast<size_t>(n) * p.D, ws.s_q);
+    WarpLists<NS> L;
+    L.init(p.KQuery);
+    V.clear();
+    Stats st{0, 0};
+
+    // query_layer.cu:55 fetch_unfiltered(d_starting_points, nullptr, S)
+    for (uint32_t i = 0; i < p.num_starting_points; i += 32) {
+      const int ck = (i + lane < p.num_starting_points) ? p.d_starting_points[i + lane] : EMPTY_KEY;
+      fetch<NS, FAST, NI, 1, false>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st);
+    }
+
+    for (uint32_t ite = 0; ite < p.max_iterations; ++ite) {
+      // :58-63
+      const float best0 = L.dist_at(0);
+      const float r_xi = (p.measure == 0) ? fminf(xi, __fmul_rn(__fmul_rn(best0, p.tau_query), p.tau_query))
+                                          : fminf(xi, __fmul_rn(best0, p.tau_query));
+      const float crit = L.dist_at(L.BEST - 1) + r_xi;
+      const int anchor = L.pop(crit);
+      if (anchor == EMPTY_KEY) break;
+      V.insert(anchor);
+      st.pops++;
+      // :69-76
+      for (uint32_t i = 0; i < p.KBuild; i += 32) {
+        const int ck = (i + lane < p.KBuild)
+                           ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane)
+                           : EMPTY_KEY;
+        fetch<NS, FAST, NI, 1, true>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st);
+      }
+    }
+
+    // :81-90 (+ simple_knn_cache.cuh:344-352)
+    const size_t row = (static_cast<size_t>(n) * p.shards_per_gpu + p.on_gpu_shard_id) * p.KQuery;
+    const int id_off = static_cast<int>(p.on_gpu_shard_id) * p.N_base;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const uint32_t k = 32u * j + lane;
+      if (k < p.KQuery) {
+        p.d_query_results[row + k] = L.key[j] + id_off;
+        if (p.d_query_results_dists) p.d_query_results_dists[row + k] = L.dist[j];
+      }
+    }
+    if (p.d_stats && lane == 0) {
+      p.d_stats[2 * static_cast<size_t>(n)] = st.pops;
+      p.d_stats[2 * static_cast<size_t>(n) + 1] = st.dists;
+    }
+
+    if (p.d_work_counter) {
+      if (lane == 0) n = atomicAdd(p.d_work_counter, 1u);
+      n = __shfl_sync(FULL, n, 0);
+    }
+    else {
+      n += total_warps;
+    }
+  }
+}
+
+template <int NS, bool FAST, int NI>
+static int launch(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream)
+{
+  auto kern = query_kernel<NS, FAST, NI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(query_kernel)");
+  kern<<<grid, a.warps_per_cta * 32, smem, stream>>>(a);
+  return set_cuda_error(cudaGetLastError(), "query_kernel launch");
+}
+
+}  // namespace g200
+
+using namespace g200;
+
+extern "C" int ggnn_b200_query_shape_init(ggnn_b200_query_shape* s, uint32_t D, uint32_t KQuery,
+                                          uint32_t max_iterations)
+{
+  // src/ggnn/query/query_kernels.cu:63-110
+  if (KQuery == 0 || KQuery > 6000) return set_error(GGNN_B200_ERR_INVALID, "KQuery must be in [1, 6000]");
+  const uint32_t required_sorted = next_multiple32(KQuery + 1 + 16);
+  const uint32_t cache = std::max({256u, required_sorted + 32u, bit_ceil_u32(max_iterations)});
+  const uint32_t cache_block = bit_ceil_u32((cache + 15) / 16);
+  const uint32_t dim_block = bit_ceil_u32((D + 3) / 4);
+  const uint32_t block = std::max({32u, cache_block, dim_block});
+  if (max_iterations > 8192) return set_error(GGNN_B200_ERR_INVALID, "max_iterations must be <= 8192");
+  if (D == 0 || D > 4096) return set_error(GGNN_B200_ERR_INVALID, "D must be in [1, 4096]");
+  if (cache > 8192 || block > 1024) return set_error(GGNN_B200_ERR_INVALID, "cache size / block size out of range");
+  s->cache_size = cache;
+  s->block_dim_x = block;
+  s->sorted_size = std::max(cache < 512u ? 64u : 32u, required_sorted);
+  return 0;
+}
+
+extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_query, ggnn_b200_stream_t stream_)
+{
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!pin) return set_error(GGNN_B200_ERR_INVALID, "null params");
+  QueryArgs a{};
+  a.p = *pin;
+  ggnn_b200_query_params& p = a.p;
+  if (!p.d_base || !p.d_query || !p.d_graph || !p.d_starting_points || !p.d_nn1_stats || !p.d_query_results)
+    return set_error(GGNN_B200_ERR_INVALID, "null device pointer");
+  if (p.measure != GGNN_B200_EUCLIDEAN && p.measure != GGNN_B200_COSINE)
+    return set_error(GGNN_B200_ERR_INVALID, "unknown distance measure");
+  if (p.shards_per_gpu == 0) p.shards_per_gpu = 1;
+  if (p.on_gpu_shard_id >= p.shards_per_gpu) return set_error(GGNN_B200_ERR_INVALID, "on_gpu_shard_id out of range");
+  ggnn_b200_query_shape shape;
+  if (int rc = ggnn_b200_query_shape_init(&shape, p.D, p.KQuery, p.max_iterations)) return rc;
+  if (!p.cache_size) p.cache_size = shape.cache_size;
+  if (!p.sorted_size) p.sorted_size = shape.sorted_size;
+  if (!p.block_dim_x) p.block_dim_x = shape.block_dim_x;
+  // query_layer.cuh:45-49
+  if (!(p.KQuery < p.sorted_size && p.sorted_size < p.cache_size))
+    return set_error(GGNN_B200_ERR_INVALID, "need KQuery < sorted_size < cache_size");
+  if (p.D > p.block_dim_x * 4) return set_error(GGNN_B200_ERR_INVALID, "D > block_dim_x * 4");
+  if (p.sorted_size % 32 || p.block_dim_x % 32) return set_error(GGNN_B200_ERR_INVALID, "sorted_size/block_dim_x must be multiples of 32");
+  if (p.KBuild == 0 || p.N_base <= 0) return set_error(GGNN_B200_ERR_INVALID, "bad KBuild / N_base");
+  if (N_query == 0) return 0;
+  const int NS = p.sorted_size / 32;
+  if (NS > 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "sorted_size > 128 (KQuery > 111) not built yet");
+  if (p.D % 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "D must be a multiple of 4 (16-byte rows for bulk copies)");
+  if (p.d_work_counter) {
+    cudaError_t e = cudaMemsetAsync(p.d_work_counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(work counter)");
+  }
+
+  const bool fast = (p.block_dim_x == 32) && (p.D % 32 == 0) && (p.D <= 128);
+  const int NI = p.D / 32;
+
+  // per-warp shared memory plan
+  const DeviceInfo& dev = device_info();
+  const uint32_t row_bytes = p.D * 4;
+  const uint32_t vcap = p.cache_size - p.sorted_size;
+  a.ring_cap = (vcap < p.max_iterations) ? vcap : 0;
+  a.hsize = std::max(64u, 2u * bit_ceil_u32(std::max(1u, p.max_iterations)));
+  const uint32_t fixed = (fast ? 0 : align_up(row_bytes, 16)) + p.sorted_size * 4 + a.hsize * 4 +
+                         align_up(a.ring_cap * 4, 16) + 16;
+  a.warps_per_cta = env_u32("GGNN_B200_QUERY_WARPS", 4);
+  const uint32_t target_warps_per_sm = env_u32("GGNN_B200_QUERY_WARPS_PER_SM", 16);
+  const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / a.warps_per_cta + 1)) / target_warps_per_sm;
+  uint32_t rows = budget > fixed ? (budget - fixed) / row_bytes : 0;
+  rows = std::min(32u, rows / 8 * 8);
+  rows = std::max(rows, 8u);
+  rows = env_u32("GGNN_B200_QUERY_STAGE_ROWS", rows);
+  if (rows % 8 || rows == 0 || rows > 32) return set_error(GGNN_B200_ERR_INVALID, "stage rows must be 8, 16, 24 or 32");
+  a.stage_rows = rows;
+  uint32_t off = align_up(rows * row_bytes, 16);
+  a.off_sq = off;
+  off += fast ? 0 : align_up(row_bytes, 16);
+  a.off_sorted = off;
+  off += p.sorted_size * 4;
+  a.off_hash = off;
+  off += a.hsize * 4;
+  a.off_ring = off;
+  off += align_up(a.ring_cap * 4, 16);
+  a.off_bar = off;
+  off += 16;
+  a.warp_smem_bytes = align_up(off, 128);
+  const size_t smem = static_cast<size_t>(a.warp_smem_bytes) * a.warps_per_cta;
+  if (smem > dev.smem_per_block_optin)
+    return set_error(GGNN_B200_ERR_UNSUPPORTED, "per-CTA shared memory exceeds the device limit for this D");
+  a.N_query = N_query;
+
+  const uint32_t ctas_needed = (N_query + a.warps_per_cta - 1) / a.warps_per_cta;
+  uint32_t grid = ctas_needed;
+  if (p.d_work_counter) {
+    const uint32_t per_sm = std::max<uint32_t>(1, std::min<uint32_t>(32, dev.smem_per_sm / (smem + 1024)));
+    grid = std::min(ctas_needed, per_sm * dev.num_sms);
+  }
+
+#define G200_LAUNCH(NS_, FAST_, NI_) return launch<NS_, FAST_, NI_>(a, grid, smem, stream)
+  if (fast) {
+    switch (NS * 10 + NI) {
+      case 11: G200_LAUNCH(1, true, 1);
+      case 12: G200_LAUNCH(1, true, 2);
+      case 13: G200_LAUNCH(1, true, 3);
+      case 14: G200_LAUNCH(1, true, 4);
+      case 21: G200_LAUNCH(2, true, 1);
+      case 22: G200_LAUNCH(2, true, 2);
+      case 23: G200_LAUNCH(2, true, 3);
+      case 24: G200_LAUNCH(2, true, 4);
+      default: break;
+    }
+  }
+  switch (NS) {
+    case 1: G200_LAUNCH(1, false, 1);
+    case 2: G200_LAUNCH(2, false, 1);
+    case 3: G200_LAUNCH(3, false, 1);
+    case 4: G200_LAUNCH(4, false, 1);
+  }
+#undef G200_LAUNCH
+  return set_error(GGNN_B200_ERR_UNSUPPORTED, "no kernel variant");
+}

@@ -1,0 +1,218 @@
+// traverse.cuh -- the per-warp "fetch" step shared by the query, merge and sym kernels:
+// filter candidate ids against the cache, stage the surviving base rows into shared memory with
+// one bulk async copy per row (all in flight together), compute all distances in the reference's
+// summation order, then apply the pushes strictly in the reference's candidate order
+// (include/ggnn/cuda_utils/simple_knn_cache.cuh:241-289).
+#pragma once
+#include "common.cuh"
+
+namespace g200 {
+
+// per-warp shared-memory working set
+struct WarpSmem {
+  float* stage;      // [stage_rows * D], 16-byte aligned
+  float* s_q;        // [D] query copy (generic distance path / sym half-way point), may be null
+  int* s_sorted;     // [32*NS] mirror of the sorted keys for the filter
+  uint64_t* bar;     // mbarrier for the bulk copies
+  uint32_t parity;   // phase of `bar`
+  uint32_t stage_rows;  // multiple of 8
+};
+
+struct Stats {
+  uint32_t pops, dists;
+};
+
+// FAST distance of up to 8 staged rows for D == 32*D32 and a reference block of VB == 32*NW threads
+// (4 dims per thread): virtual thread (w, lane) owns the 32-float chunks c = w, w+NW, w+2NW, ...
+// (dims 32*c + lane), accumulated in that order; each virtual warp w is tree-reduced, the warp
+// aggregates are added sequentially (cub::BlockReduce).  Lane l gets row (l & 7).
+template <int D32, int NW>
+__device__ __forceinline__ float dist8_fast(const float* __restrict__ rows, int nrows, int measure,
+                                            const float (&q)[D32], float q_norm)
+{
+  const int lane = lane_id();
+  constexpr int D = 32 * D32;
+  if (measure == 0) {
+    float v[NW][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) v[w][i] = 0.f;
+      if (i < nrows) {
+        const float* rp = rows + i * D + lane;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          float acc = 0.f;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int c = it * NW + w;
+            if (c < D32) {
+              const float diff = rp[32 * c] - q[c];
+              acc = fmaf(diff, diff, acc);
+            }
+          }
+          v[w][i] = acc;
+        }
+      }
+    }
+    float tot = warp_tree_sum8(v[0]);
+#pragma unroll
+    for (int w = 1; w < NW; ++w) tot = tot + warp_tree_sum8(v[w]);
+    return tot;
+  }
+  float dot_t = 0.f, nrm_t = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    float vd[8], vn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float dot = 0.f, nrm = 0.f;
+      if (i < nrows) {
+        const float* rp = rows + i * D + lane;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int c = it * NW + w;
+          if (c < D32) {
+            const float b = rp[32 * c];
+            dot = __fadd_rn(dot, __fmul_rn(b, q[c]));  // not fused in the reference (see oracle header)
+            nrm = __fadd_rn(nrm, __fmul_rn(b, b));
+          }
+        }
+      }
+      vd[i] = dot;
+      vn[i] = nrm;
+    }
+    const float sd = warp_tree_sum8(vd), sn = warp_tree_sum8(vn);
+    dot_t = (w == 0) ? sd : dot_t + sd;
+    nrm_t = (w == 0) ? sn : nrm_t + sn;
+  }
+  return cosine_finish(dot_t, nrm_t, q_norm);
+}
+
+// Query-side state needed for distances.  FAST: q[c] = query[32*c + lane].
+template <bool FAST, int D32, int NW>
+struct QueryVec {
+  float q[FAST ? D32 : 1];
+  float q_norm;
+  DistCfg cfg;
+  const float* s_q;
+
+  __device__ __forceinline__ void load(const DistCfg& c, const float* __restrict__ g_q, float* smem_q)
+  {
+    cfg = c;
+    const int lane = lane_id();
+    q_norm = 0.f;
+    if constexpr (FAST) {
+      s_q = nullptr;
+#pragma unroll
+      for (int ch = 0; ch < D32; ++ch) q[ch] = g_q[lane + 32 * ch];
+      if (c.measure != 0) {  // distance.cuh:104-117
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          float a = 0.f;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int ch = it * NW + w;
+            if (ch < D32) a = fmaf(q[ch], q[ch], a);
+          }
+          a = warp_tree_sum(a);
+          tot = (w == 0) ? a : tot + a;
+        }
+        q_norm = tot;
+      }
+    }
+    else {
+      __syncwarp();
+      for (uint32_t d = lane; d < c.D; d += 32) smem_q[d] = g_q[d];
+      __syncwarp();
+      s_q = smem_q;
+      if (c.measure != 0) q_norm = query_norm_generic(c, smem_q);
+    }
+  }
+};
+
+// Stage the rows of candidates [b0, b0+nb) (lane b0+r holds base row index m of local row r) and
+// return this lane's distance (valid for lanes in [b0, b0+nb)).  b0 % 8 == 0.
+template <bool FAST, int D32, int NW>
+__device__ __forceinline__ float stage_and_dist(WarpSmem& ws, const QueryVec<FAST, D32, NW>& qv,
+                                                const float* __restrict__ base, int m, int b0, int nb)
+{
+  const int lane = lane_id();
+  const uint32_t D = qv.cfg.D;
+  const uint32_t row_bytes = D * 4u;
+  if (lane == 0) mbar_expect_tx(ws.bar, row_bytes * nb);
+  __syncwarp();
+  const int r = lane - b0;
+  if (r >= 0 && r < nb) bulk_g2s(ws.stage + static_cast<size_t>(r) * D, base + static_cast<size_t>(m) * D, row_bytes, ws.bar);
+  mbar_wait(ws.bar, ws.parity);
+  ws.parity ^= 1;
+
+  float mine = G200_INF;
+  if constexpr (FAST) {
+    for (int g = 0; g * 8 < nb; ++g) {
+      const float dg = dist8_fast<D32, NW>(ws.stage + g * 8 * D, nb - g * 8, qv.cfg.measure, qv.q, qv.q_norm);
+      if ((r >> 3) == g) mine = dg;
+    }
+  }
+  else {
+    for (int i = 0; i < nb; ++i) {
+      float a, b;
+      dist_partials_generic(qv.cfg, ws.stage + static_cast<size_t>(i) * D, qv.s_q, a, b);
+      const float d = qv.cfg.measure == 0 ? a : cosine_finish(a, b, qv.q_norm);
+      if (r == i) mine = d;
+    }
+  }
+  __syncwarp();  // all reads of the stage are done before the next batch overwrites it
+  return mine;
+}
+
+// One fetch of up to 32 candidate ids (ck per lane, EMPTY_KEY = none).
+//   FILTER  : drop ids present in best list / prioQ / visited set (simple_knn_cache.cuh:246-261)
+//   xi      : criteria() = dist[BEST-1] + xi, re-read after every push (:284)
+template <int NS, bool FAST, int D32, int NW, bool FILTER>
+__device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, WarpSmem& ws,
+                                      const QueryVec<FAST, D32, NW>& qv, const float* __restrict__ base,
+                                      const int* __restrict__ translation, int ck, float xi, Stats& st)
+{
+  const int lane = lane_id();
+  bool valid = ck != EMPTY_KEY;
+  if constexpr (FILTER) {
+    __syncwarp();
+    L.store_keys(ws.s_sorted);
+    __syncwarp();
+    if (valid) valid = !WarpLists<NS>::in_sorted(ws.s_sorted, ck) && !V.contains(ck);
+  }
+  const unsigned mask = __ballot_sync(FULL, valid);
+  const int cnt = __popc(mask);
+  if (cnt == 0) return;
+  st.dists += cnt;
+
+  // compact: lane r <- r-th surviving candidate (adjacency order preserved)
+  const unsigned src = __fns(mask, 0, lane + 1);
+  const int key_r = __shfl_sync(FULL, ck, src & 31);
+  int m = 0;
+  if (lane < cnt) m = translation ? translation[key_r] : key_r;
+
+  float mine = G200_INF;
+  for (int b0 = 0; b0 < cnt; b0 += ws.stage_rows) {
+    const int nb = min(static_cast<int>(ws.stage_rows), cnt - b0);
+    const float d = stage_and_dist<FAST, D32, NW>(ws, qv, base, m, b0, nb);
+    if (lane >= b0 && lane < b0 + nb) mine = d;
+  }
+
+  // pushes in candidate order; criteria re-evaluated after each push
+  unsigned rem = cnt >= 32 ? FULL : ((1u << cnt) - 1u);
+  while (true) {
+    const float crit = L.dist_at(L.BEST - 1) + xi;
+    const unsigned pm = __ballot_sync(FULL, mine < crit) & rem;
+    if (!pm) break;
+    const int c0 = __ffs(pm) - 1;
+    const int k = __shfl_sync(FULL, key_r, c0);
+    const float d = __shfl_sync(FULL, mine, c0);
+    L.push(k, d);
+    rem &= ~((2u << c0) - 1u);
+  }
+}
+
+}  // namespace g200

@@ -1,0 +1,173 @@
+/*
+ * ggnn_b200.h -- C ABI of libggnn_b200.so: the B200 (sm_100a) implementation of GGNN's batched
+ * query hot path and graph-construction kernels.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every kernel entry
+ * point carries exactly the fields of the reference's by-value kernel parameter aggregate it
+ * replaces (cited per struct, paths relative to the reference tree), is asynchronous on the given
+ * CUDA stream, allocates nothing, keeps no global mutable state and requires the right device to
+ * be current -- the same contract as the reference's thin host->CUDA boundary
+ * (include/ggnn/query/query_kernels.cuh:47-57, include/ggnn/construction/graph_construction.cuh:41-55).
+ *
+ * All device pointers must be 16-byte aligned.  Keys are int32, distances fp32, base vectors fp32.
+ * Return value: 0 (cudaSuccess) or a cudaError_t / GGNN_B200_ERR_* code; the message of the last
+ * error of the calling thread is available from ggnn_b200_last_error().
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef GGNN_B200_H
+#define GGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGNN_B200_EUCLIDEAN 0 /* include/ggnn/base/def.h:27-30 */
+#define GGNN_B200_COSINE 1
+#define GGNN_B200_L 4 /* include/ggnn/base/graph_config.h:42-43 */
+
+#define GGNN_B200_ERR_INVALID 10001     /* precondition the reference CHECKs (would abort there) */
+#define GGNN_B200_ERR_UNSUPPORTED 10002 /* valid in the reference, not built here yet */
+
+typedef void* ggnn_b200_stream_t; /* cudaStream_t */
+
+const char* ggnn_b200_last_error(void);
+/* "sm_100a" + build info; never NULL */
+const char* ggnn_b200_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph configuration / blob layout (host only).
+ * Replaces ggnn::GraphConfig (include/ggnn/base/graph_config.h:32-107, src/ggnn/base/graph_config.cpp:39-98)
+ * and ggnn::Graph::PartSizes / layout (include/ggnn/base/graph.h:38-55, src/ggnn/base/graph.cpp:33-92).
+ * The blob is byte-compatible with the reference's part_<id>.ggnn files.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t N, D, KBuild;
+  uint32_t KF, G, S, S0, S0_off, SG, SG_off;
+  uint32_t N_all, ST_all;
+  uint32_t Bs[GGNN_B200_L], Ns[GGNN_B200_L], Ns_offsets[GGNN_B200_L], STs_offsets[GGNN_B200_L];
+} ggnn_b200_graph_config;
+
+int ggnn_b200_graph_config_init(ggnn_b200_graph_config* cfg, uint32_t N, uint32_t D, uint32_t KBuild);
+size_t ggnn_b200_graph_blob_bytes(const ggnn_b200_graph_config* cfg);
+/* byte offsets of the parts inside the blob: neighbourhoods [N_all,K] | translation [ST_all] |
+ * selection [ST_all] | nn1_stats [2] */
+typedef struct {
+  size_t graph, translation, selection, nn1_stats, total;
+} ggnn_b200_graph_offsets;
+void ggnn_b200_graph_blob_offsets(const ggnn_b200_graph_config* cfg, ggnn_b200_graph_offsets* out);
+/* scratch needed by ggnn_b200_build_graph (replaces GraphBuffer, src/ggnn/construction/graph_buffer.cu:38-81) */
+size_t ggnn_b200_build_scratch_bytes(const ggnn_b200_graph_config* cfg);
+
+/* derived launch shape of the reference's query kernel (src/ggnn/query/query_kernels.cu:77-110).
+ * block_dim_x fixes the floating-point summation order of every distance (cub::BlockReduce over
+ * block_dim_x threads, 4 dims per thread), so it is part of the results contract. */
+typedef struct {
+  uint32_t cache_size, sorted_size, block_dim_x;
+} ggnn_b200_query_shape;
+int ggnn_b200_query_shape_init(ggnn_b200_query_shape* s, uint32_t D, uint32_t KQuery, uint32_t max_iterations);
+
+/* ------------------------------------------------------------------------------------------------
+ * ANN query.  Replaces ggnn::QueryKernel (include/ggnn/query/query_layer.cuh:56-85,
+ * src/ggnn/query/query_layer.cu:39-97) and its launcher QueryKernelsImpl::query
+ * (src/ggnn/query/query_kernels.cu:50-186).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t D;
+  int32_t measure;
+  uint32_t KQuery;
+  uint32_t sorted_size; /* 0 = derive like the reference */
+  uint32_t cache_size;  /* 0 = derive like the reference */
+  uint32_t block_dim_x; /* 0 = derive like the reference */
+  float tau_query;
+  uint32_t max_iterations;
+  int32_t N_base;
+  uint32_t KBuild;
+  uint32_t num_starting_points;
+  const float* d_base;              /* [N_base, D] */
+  const float* d_query;             /* [N_query, D] */
+  const int32_t* d_graph;           /* [N_base, KBuild] layer-0 neighbourhoods */
+  const int32_t* d_starting_points; /* [num_starting_points] = translation[L-1] */
+  const float* d_nn1_stats;         /* [2] = {mean, max} */
+  int32_t* d_query_results;         /* [N_query, KQuery * shards_per_gpu] */
+  float* d_query_results_dists;     /* same shape; may be NULL */
+  uint32_t* d_stats;                /* optional [N_query, 2] = {pops, distance evaluations} (reference: d_dist_stats, dead) */
+  uint32_t shards_per_gpu;          /* >= 1 */
+  uint32_t on_gpu_shard_id;
+  uint32_t* d_work_counter;         /* optional device uint32 used for dynamic query scheduling
+                                       (zeroed by the call on `stream`); NULL = static mapping */
+} ggnn_b200_query_params;
+
+int ggnn_b200_query(const ggnn_b200_query_params* p, uint32_t N_query, ggnn_b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Brute-force query.  Replaces ggnn::BruteForceQueryKernel (include/ggnn/query/bf_query_layer.cuh:54-64,
+ * src/ggnn/query/bf_query_layer.cu:39-65) and QueryKernelsImpl::bruteForceQuery (query_kernels.cu:188-264).
+ * Results are the K smallest (distance, index) pairs in the reference's own fp32 arithmetic.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t D;
+  int32_t measure;
+  uint32_t KQuery;
+  int32_t N_base;
+  const float* d_base;          /* [N_base, D] */
+  const float* d_query;         /* [N_query, D] */
+  int32_t* d_query_results;     /* [N_query, KQuery] */
+  float* d_query_results_dists; /* [N_query, KQuery]; may be NULL */
+} ggnn_b200_bf_query_params;
+
+int ggnn_b200_bf_query(const ggnn_b200_bf_query_params* p, uint32_t N_query, ggnn_b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph construction kernels (one entry point per reference kernel) and the full schedule.
+ * d_graph_blob is a device blob laid out by ggnn_b200_graph_blob_offsets().
+ * ---------------------------------------------------------------------------------------------- */
+/* TopMergeKernel: include/ggnn/construction/top_merge_layer.cuh:48-61, src/.../top_merge_layer.cu:40-82 */
+int ggnn_b200_top(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, uint32_t layer,
+                  void* d_graph_blob, float* d_nn1_dist_buffer, ggnn_b200_stream_t stream);
+/* cub::DeviceReduce Sum/Max + divide: src/ggnn/construction/graph_construction.cu:381-393, 79-83.
+ * d_scratch: >= 8 KiB */
+int ggnn_b200_nn1_stats(const float* d_nn1_dist_buffer, uint32_t N, float* d_nn1_stats, void* d_scratch,
+                        ggnn_b200_stream_t stream);
+/* WRSSelectionKernel: include/.../wrs_select_layer.cuh:51-66, src/.../wrs_select_layer.cu:41-102.
+ * d_rng: Ns[layer] uniforms in (0,1] */
+int ggnn_b200_select(const ggnn_b200_graph_config* cfg, uint32_t layer, const float* d_nn1_dist_buffer,
+                     const float* d_rng, void* d_graph_blob, ggnn_b200_stream_t stream);
+/* MergeKernel + publish copy: include/.../merge_layer.cuh:61-88, src/.../merge_layer.cu:39-158,
+ * graph_construction.cu:240-296.  d_graph_buffer: [Ns[layer_btm], KBuild] scratch */
+int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, float tau_build,
+                    uint32_t layer_top, uint32_t layer_btm, void* d_graph_blob, int32_t* d_graph_buffer,
+                    float* d_nn1_dist_buffer, ggnn_b200_stream_t stream);
+/* SymQueryKernel (+ the two memsets before it): include/.../sym_query_layer.cuh:54-70,
+ * src/.../sym_query_layer.cu:39-145, graph_construction.cu:298-352 */
+int ggnn_b200_sym(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, float tau_build,
+                  uint32_t layer, void* d_graph_blob, int32_t* d_sym_buffer, uint32_t* d_sym_atomic,
+                  ggnn_b200_stream_t stream);
+/* SymBufferMergeKernel: include/.../sym_buffer_merge_layer.cuh:45-53, src/.../sym_buffer_merge_layer.cu:36-99 */
+int ggnn_b200_sym_buffer_merge(const ggnn_b200_graph_config* cfg, uint32_t layer, const int32_t* d_sym_buffer,
+                               const uint32_t* d_sym_atomic, void* d_graph_blob, ggnn_b200_stream_t stream);
+/* GraphConstruction::build + refine x refinement_iterations (graph_construction.cu:128-147,
+ * gpu_instance.cu:550-555).  d_rng: NULL = draw with cuRAND XORWOW seed 1234 like the reference
+ * (graph_construction.cu:96-102,168-169); else Ns[0]+Ns[1]+Ns[2] uniforms consumed layer by layer. */
+int ggnn_b200_build_graph(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, float tau_build,
+                          uint32_t refinement_iterations, const float* d_rng, void* d_graph_blob, void* d_scratch,
+                          size_t scratch_bytes, ggnn_b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Shard merge.  Replaces the per-GPU cub::DeviceSegmentedRadixSort (src/ggnn/base/gpu_instance.cu:745-790)
+ * and the CPU heap merge ResultMerger::merge (src/ggnn/base/result_merger.cpp:51-149) with one kernel:
+ * n_lists sorted runs of K_in (id, dist) per query -> the K smallest.  List l of query n starts at
+ * d_ids + (l * list_stride + n * query_stride); ids get id_offset_per_list * l added
+ * (result_merger.cpp:115-116).  Ties: lower list index first (the reference's order is arbitrary).
+ * ---------------------------------------------------------------------------------------------- */
+int ggnn_b200_merge_topk(const int32_t* d_ids, const float* d_dists, uint32_t n_lists, size_t list_stride,
+                         size_t query_stride, uint32_t K_in, uint32_t N_query, uint32_t K,
+                         int64_t id_offset_per_list, int32_t* d_out_ids, float* d_out_dists,
+                         ggnn_b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

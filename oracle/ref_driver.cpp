@@ -1,0 +1,198 @@
+// ref_driver -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the UNMODIFIED reference library (oracle/_ref/libggnn_ref.so, built from
+// /root/reference by oracle/build_ref.sh) through its own public API ggnn::GGNN
+// (include/ggnn/base/ggnn.cuh:41-182) to (a) produce golden dumps (graph blob, query / bf_query
+// ids + dists) for the parity tests and (b) time the reference CUDA path on the same box for
+// bench.py --impl reference.  This file is written for this repo; it contains no reference code.
+//
+// usage: ref_driver key=value ...
+//   dir=<workdir>            working directory: base.bin, query.bin (raw fp32 row-major) are read
+//                            from it, part_0.ggnn is stored to / loaded from it, dumps go to it
+//   n=<N_base> nq=<N_query> d=<D>
+//   measure=0|1              0 Euclidean, 1 Cosine
+//   kbuild=24 tau_build=0.5 refine=2
+//   build=1|0                1: build() + store();  0: load(kbuild) from dir/part_0.ggnn
+//   kquery=10 tau_query=0.64 max_iter=400
+//   query_reps=R             run query() R times from pinned host memory (end to end), report each
+//   gpu_reps=R               run query() R times with the query resident on the GPU and results
+//                            left on the GPU (kernel + result allocation only)
+//   bf=K                     run bfQuery(K) once (0 = skip), dump bf_ids.bin / bf_dists.bin
+//   dump=1|0                 write query_ids.bin / query_dists.bin
+#include <ggnn/base/ggnn.cuh>
+#include <ggnn/base/eval.h>
+
+#include <glog/logging.h>
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+using namespace ggnn;
+using Clock = std::chrono::steady_clock;
+
+static std::map<std::string, std::string> parse(int argc, char** argv)
+{
+  std::map<std::string, std::string> m;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto p = a.find('=');
+    if (p == std::string::npos) continue;
+    m[a.substr(0, p)] = a.substr(p + 1);
+  }
+  return m;
+}
+static std::string gets(const std::map<std::string, std::string>& m, const char* k, const char* d)
+{
+  auto it = m.find(k);
+  return it == m.end() ? d : it->second;
+}
+static double getd(const std::map<std::string, std::string>& m, const char* k, double d)
+{
+  auto it = m.find(k);
+  return it == m.end() ? d : atof(it->second.c_str());
+}
+
+static std::vector<float> read_f32(const std::filesystem::path& p, size_t count)
+{
+  std::vector<float> v(count);
+  std::ifstream f(p, std::ios::binary);
+  if (!f) { fprintf(stderr, "cannot open %s\n", p.c_str()); exit(2); }
+  f.read(reinterpret_cast<char*>(v.data()), count * sizeof(float));
+  if (static_cast<size_t>(f.gcount()) != count * sizeof(float)) { fprintf(stderr, "short read %s\n", p.c_str()); exit(2); }
+  return v;
+}
+template <typename T>
+static void write_bin(const std::filesystem::path& p, const T* data, size_t count)
+{
+  std::ofstream f(p, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(data), count * sizeof(T));
+}
+
+// collects the reference's own "query part ... => ms: X" VLOG(0) lines (gpu_instance.cu:709-712)
+struct CerrCapture {
+  std::stringstream ss;
+  std::streambuf* old;
+  CerrCapture() : old(std::cerr.rdbuf(ss.rdbuf())) {}
+  ~CerrCapture() { std::cerr.rdbuf(old); }
+  std::vector<double> values(const std::string& tag)
+  {
+    std::vector<double> out;
+    std::string s = ss.str(), line;
+    std::stringstream in(s);
+    while (std::getline(in, line)) {
+      auto p = line.find(tag);
+      if (p != std::string::npos) out.push_back(atof(line.c_str() + p + tag.size()));
+    }
+    return out;
+  }
+};
+
+int main(int argc, char** argv)
+{
+  auto a = parse(argc, argv);
+  const std::filesystem::path dir = gets(a, "dir", ".");
+  const size_t N = static_cast<size_t>(getd(a, "n", 10000));
+  const size_t Nq = static_cast<size_t>(getd(a, "nq", 10000));
+  const uint32_t D = static_cast<uint32_t>(getd(a, "d", 128));
+  const auto measure = getd(a, "measure", 0) ? DistanceMeasure::Cosine : DistanceMeasure::Euclidean;
+  const uint32_t kbuild = static_cast<uint32_t>(getd(a, "kbuild", 24));
+  const float tau_build = static_cast<float>(getd(a, "tau_build", 0.5));
+  const uint32_t refine = static_cast<uint32_t>(getd(a, "refine", 2));
+  const bool do_build = getd(a, "build", 1) != 0;
+  const uint32_t kquery = static_cast<uint32_t>(getd(a, "kquery", 10));
+  const float tau_query = static_cast<float>(getd(a, "tau_query", 0.64));
+  const uint32_t max_iter = static_cast<uint32_t>(getd(a, "max_iter", 400));
+  const int query_reps = static_cast<int>(getd(a, "query_reps", 1));
+  const int gpu_reps = static_cast<int>(getd(a, "gpu_reps", 0));
+  const uint32_t bf = static_cast<uint32_t>(getd(a, "bf", 0));
+  const bool dump = getd(a, "dump", 1) != 0;
+
+  google::SetVLOGLevel("*", 0);
+
+  std::vector<float> base_v = read_f32(dir / "base.bin", N * D);
+  std::vector<float> query_v = read_f32(dir / "query.bin", Nq * D);
+  Dataset<float> base = Dataset<float>::copy(base_v, D, true);
+  Dataset<float> query = Dataset<float>::copy(query_v, D, true);
+
+  printf("{\"impl\": \"reference\", \"n\": %zu, \"nq\": %zu, \"d\": %u", N, Nq, D);
+
+  GGNN<int32_t, float> ggnn{};
+  ggnn.setWorkingDirectory(dir);
+  ggnn.setBaseReference(base);
+
+  if (do_build) {
+    const auto t0 = Clock::now();
+    ggnn.build(kbuild, tau_build, refine, measure);
+    cudaDeviceSynchronize();
+    const double s = std::chrono::duration<double>(Clock::now() - t0).count();
+    ggnn.store();
+    printf(", \"build_s\": %.6f", s);
+  }
+  else {
+    ggnn.load(kbuild);
+  }
+
+  if (bf) {
+    const auto t0 = Clock::now();
+    auto res = ggnn.bfQuery(query, bf, measure);
+    cudaDeviceSynchronize();
+    const double s = std::chrono::duration<double>(Clock::now() - t0).count();
+    printf(", \"bf_s\": %.6f", s);
+    write_bin(dir / "bf_ids.bin", res.ids.data(), Nq * bf);
+    write_bin(dir / "bf_dists.bin", res.dists.data(), Nq * bf);
+  }
+
+  if (query_reps > 0) {
+    printf(", \"query_e2e_ms\": [");
+    std::vector<double> kernel_ms;
+    for (int r = 0; r < query_reps; ++r) {
+      CerrCapture cap;
+      const auto t0 = Clock::now();
+      auto res = ggnn.query(query, kquery, tau_query, max_iter, measure);
+      const double ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+      printf("%s%.4f", r ? ", " : "", ms);
+      for (double v : cap.values("=> ms: ")) kernel_ms.push_back(v);
+      if (dump && r == query_reps - 1) {
+        write_bin(dir / "query_ids.bin", res.ids.data(), Nq * kquery);
+        write_bin(dir / "query_dists.bin", res.dists.data(), Nq * kquery);
+      }
+    }
+    printf("], \"query_kernel_ms\": [");
+    for (size_t i = 0; i < kernel_ms.size(); ++i) printf("%s%.4f", i ? ", " : "", kernel_ms[i]);
+    printf("]");
+  }
+
+  if (gpu_reps > 0) {
+    ggnn.setReturnResultsOnGPU(true);
+    Dataset<float> q_gpu = Dataset<float>::emptyOnGPU(Nq, D, 0);
+    query.copyTo(q_gpu);
+    cudaDeviceSynchronize();
+    printf(", \"query_gpu_ms\": [");
+    std::vector<double> kernel_ms;
+    for (int r = 0; r < gpu_reps; ++r) {
+      CerrCapture cap;
+      const auto t0 = Clock::now();
+      auto res = ggnn.query(q_gpu, kquery, tau_query, max_iter, measure);
+      cudaDeviceSynchronize();
+      const double ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+      printf("%s%.4f", r ? ", " : "", ms);
+      for (double v : cap.values("=> ms: ")) kernel_ms.push_back(v);
+    }
+    printf("], \"query_gpu_kernel_ms\": [");
+    for (size_t i = 0; i < kernel_ms.size(); ++i) printf("%s%.4f", i ? ", " : "", kernel_ms[i]);
+    printf("]");
+  }
+  printf("}\n");
+  fflush(stdout);
+  return 0;
+}
