@@ -19,6 +19,7 @@
 //                            left on the GPU (kernel + result allocation only)
 //   bf=K                     run bfQuery(K) once (0 = skip), dump bf_ids.bin / bf_dists.bin
 //   dump=1|0                 write query_ids.bin / query_dists.bin
+//   gpus=G shard=N_shard     use GPUs 0..G-1 and shards of N_shard rows (default: 1 GPU, one shard)
 #include <ggnn/base/ggnn.cuh>
 #include <ggnn/base/eval.h>
 
@@ -128,6 +129,14 @@ int main(int argc, char** argv)
 
   GGNN<int32_t, float> ggnn{};
   ggnn.setWorkingDirectory(dir);
+  {
+    const int gpus = static_cast<int>(getd(a, "gpus", 1));
+    std::vector<int> ids;
+    for (int i = 0; i < gpus; ++i) ids.push_back(i);
+    ggnn.setGPUs(ids);
+    const uint32_t shard = static_cast<uint32_t>(getd(a, "shard", 0));
+    if (shard) ggnn.setShardSize(shard);
+  }
   ggnn.setBaseReference(base);
 
   if (do_build) {

@@ -1,0 +1,97 @@
+"""Host-side logic of the Python mirror of the reference API (no GPU): argument checks, sharding rules,
+Evaluator, dataset IO, result-merge semantics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ggnn_b200 as ggnn
+from ggnn_b200 import distributed as D
+from oracle import pyoracle as O
+
+
+def test_api_surface_matches_reference_module():
+    # nanobind.cu:131-301
+    for name in ("GGNN", "DistanceMeasure", "Evaluator", "Evaluation", "FloatDataset", "UCharDataset", "IntDataset",
+                 "set_log_level"):
+        assert hasattr(ggnn, name)
+    g = ggnn.GGNN()
+    for m in ("set_base", "set_working_directory", "set_cpu_memory_limit", "set_reserved_gpu_memory", "set_gpus",
+              "set_shard_size", "set_return_results_on_gpu", "build", "load", "store", "query", "bf_query", "get_graph"):
+        assert callable(getattr(g, m))
+    assert int(ggnn.DistanceMeasure.Euclidean) == 0 and int(ggnn.DistanceMeasure.Cosine) == 1
+
+
+def test_misuse_raises_like_the_reference():
+    g = ggnn.GGNN()
+    with pytest.raises(RuntimeError):
+        g.build(24, 0.5)                      # base not set (ggnn.cu:209)
+    with pytest.raises(RuntimeError):
+        g.query(torch.zeros(4, 8), 10, 0.5)   # no graph (ggnn.cu:282)
+    with pytest.raises(RuntimeError):
+        g.store()
+    with pytest.raises(ValueError):
+        g.set_base(torch.zeros(10, 5000))     # D > 4096
+    with pytest.raises(NotImplementedError):
+        g.set_base(torch.zeros(10, 8, dtype=torch.uint8))
+    g.set_base(torch.zeros(100, 8))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            g.build(24, 0.5)
+
+
+def test_shard_layout_rules():
+    assert D.shard_layout(100, 25, 2) == (4, 2)       # ggnn_main_multi_gpu.cpp:62-65 shape
+    assert D.shard_layout(100_000_000, 12_500_000, 8) == (8, 1)
+    assert D.local_rows(3, 100_000_000, 12_500_000, 8) == (37_500_000, 50_000_000)
+    assert D.local_rows(1, 100, 25, 2) == (50, 100)
+    with pytest.raises(ValueError):
+        D.shard_layout(100, 30, 2)   # N % N_shard != 0
+    with pytest.raises(ValueError):
+        D.shard_layout(100, 20, 2)   # 5 shards on 2 GPUs
+
+
+def test_evaluator_matches_oracle_restatement():
+    rng = np.random.default_rng(3)
+    base = rng.random((500, 16), dtype=np.float32)
+    base[10] = base[11]                       # exact duplicates -> duplicate-aware metrics differ
+    query = rng.random((40, 16), dtype=np.float32)
+    query[0] = base[10]
+    gt, _ = O.bf_query(base, query, 20)
+    res = gt[:, :10].copy()
+    res[::3, 2] = 499
+    res[0, 0] = gt[0, 1]
+    for measure in (0, 1):
+        e = ggnn.Evaluator(base, query, gt, 10, measure).evaluate_results(res)
+        o = O.evaluate(gt, res, 10, base, query, measure)
+        got = dict(c1=e.c1, c1_dup=e.c1_dup, cK=e.c_k_query, cK_dup=e.c_k_query_dup, rK=e.r_k_query, rK_dup=e.r_k_query_dup)
+        for k in o:
+            assert got[k] == pytest.approx(o[k], abs=1e-6), (measure, k)
+    e = ggnn.Evaluator(None, None, gt, 10).evaluate_results(res)
+    assert np.isnan(e.c1_dup) and e.c_k_query == pytest.approx(O.evaluate(gt, res, 10)["cK"], abs=1e-6)
+    assert "c@10" in repr(e)
+
+
+def test_fvecs_roundtrip(tmp_path):
+    x = torch.rand(7, 5)
+    p = os.path.join(tmp_path, "x.fvecs")
+    ggnn.FloatDataset(x).store(p)
+    raw = np.fromfile(p, dtype=np.int32)
+    assert raw[0] == 5 and raw.size == 7 * 6    # dataset.cu:118-233: [int32 D][D values] per row
+    y = ggnn.FloatDataset.load(p)
+    assert torch.equal(x, y.tensor) and (y.N, y.D) == (7, 5)
+    z = ggnn.FloatDataset.load(p, 2, 3)
+    assert torch.equal(x[2:5], z.tensor)
+    i = torch.randint(0, 1000, (4, 3), dtype=torch.int32)
+    p2 = os.path.join(tmp_path, "g.ivecs")
+    ggnn.IntDataset(i).store(p2)
+    assert torch.equal(ggnn.IntDataset.load(p2).tensor, i)
+
+
+def test_oracle_merge_semantics():
+    ids = np.array([[[0, 1, 2]], [[0, 1, 2]]], np.int32)               # 2 partitions, 1 query, K_in 3
+    d = np.array([[[0.1, 0.4, 0.9]], [[0.2, 0.4, 0.5]]], np.float32)
+    oi, od = O.merge_results(ids, d, 3, 1000)
+    assert od.tolist() == [[np.float32(0.1), np.float32(0.2), np.float32(0.4)]]
+    assert oi.tolist() == [[0, 1000, 1]]  # tie 0.4: lower partition first; ids re-based (result_merger.cpp:115-116)

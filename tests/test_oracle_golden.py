@@ -1,0 +1,119 @@
+"""The CPU oracle is pinned against (a) the reference's own GraphConfig known answers (SURVEY.md 8c,
+produced by compiling src/ggnn/base/graph_config.cpp) and (b) outputs of the UNMODIFIED reference library
+run on a B200 (tests/golden/*.npz, see tests/golden/README.md)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+
+# N, K, KF, S, G, S0, S0_off, SG, SG_off, Bs, Ns, N_all, ST_all, blob bytes  
+KAT = [
+    (10_000, 24, 12, 32, 7, 29, 53, 4, 4, [343, 49, 7, 1], [10000, 1568, 224, 32], 11_824, 1_824, 1_149_704),
+    (25_000, 24, 12, 32, 9, 34, 214, 3, 5, [729, 81, 9, 1], [25000, 2592, 288, 32], 27_912, 2_912, 2_702_856),
+    (100_000, 24, 12, 32, 15, 29, 2125, 2, 2, [3375, 225, 15, 1], [100000, 7200, 480, 32], 107_712, 7_712, 10_402_056),
+    (1_000_000, 24, 12, 32, 32, 30, 16960, 1, 0, [32768, 1024, 32, 1], [1000000, 32768, 1024, 32], 1_033_824, 33_824, 99_517_704),
+    (10_000_000, 24, 12, 32, 68, 31, 252608, 0, 32, [314432, 4624, 68, 1], [10000000, 147968, 2176, 32], 10_150_176, 150_176, 975_618_312),
+    (12_500_000, 24, 12, 32, 73, 32, 51456, 0, 32, [389017, 5329, 73, 1], [12500000, 170528, 2336, 32], 12_672_896, 172_896, 1_217_981_192),
+    (100_000_000, 24, 12, 32, 146, 32, 411648, 0, 32, [3112136, 21316, 146, 1], [100000000, 682112, 4672, 32], 100_686_816, 686_816, 9_671_428_872),
+    (1_000_000, 40, 20, 32, 31, 33, 16897, 1, 1, [29791, 961, 31, 1], [1000000, 30752, 992, 32], 1_031_776, 31_776, 165_338_376),
+    (1_000_000, 96, 48, 64, 25, 64, 0, 2, 14, [15625, 625, 25, 1], [1000000, 40000, 1600, 64], 1_041_664, 41_664, 400_332_296),
+]
+
+
+@pytest.mark.parametrize("row", KAT, ids=[f"N{r[0]}_K{r[1]}" for r in KAT])
+def test_graph_config_known_answers(row):
+    N, K, KF, S, G, S0, S0_off, SG, SG_off, Bs, Ns, N_all, ST_all, blob = row
+    c = O.graph_config(N, 128, K)
+    assert (c.KF, c.S, c.G, c.S0, c.S0_off, c.SG, c.SG_off) == (KF, S, G, S0, S0_off, SG, SG_off)
+    assert list(c.Bs) == Bs and list(c.Ns) == Ns
+    assert (c.N_all, c.ST_all) == (N_all, ST_all)
+    assert O.blob_bytes(c) == blob
+
+
+def test_launch_parameter_table():
+    # SURVEY.md appendix B (query_kernels.cu:77-110 evaluated by hand)
+    assert O.query_launch_params(128, 10, 400) == (512, 32, 32)
+    assert O.query_launch_params(96, 10, 400) == (512, 32, 32)
+    assert O.query_launch_params(128, 10, 200) == (256, 64, 32)
+    assert O.query_launch_params(128, 100, 400) == (512, 128, 32)
+    assert O.query_launch_params(128, 10, 1000) == (1024, 32, 64)
+    assert O.query_launch_params(256, 10, 400) == (512, 32, 64)
+    assert O.bf_block_dim(128) == 32 and O.bf_block_dim(960) == 256
+    assert O.construction_config(128, 128) == (128, 4) and O.construction_config(2048, 64) == (256, 8)
+
+
+def test_push_ring_wrap_quirk_trace():
+    """with a wrapped ring, push loses the entry at physical slot SORTED-1 and
+    duplicates the one at physical BEST (simple_knn_cache.cuh:160-211)."""
+    c = O.Cache(10, 32, 512, xi=1e9)
+    for i in range(10):
+        c.push(100 + i, float(i))
+    for _ in range(10):
+        assert c.pop() >= 0
+    for i in range(22):
+        c.push(200 + i, 20.0 + i)
+    keys, d, head, _ = c.state()
+    assert head == 20
+    c.push(999, 25.5)
+    keys, d, head, _ = c.state()
+    order = [(int(keys[10 + (head - 10 + j) % 22]), float(d[10 + (head - 10 + j) % 22])) for j in range(22)]
+    expect = [(200, 20.0), (201, 21.0), (202, 22.0), (203, 23.0), (204, 24.0), (205, 25.0), (999, 25.5), (206, 26.0),
+              (207, 27.0), (208, 28.0), (209, 29.0), (210, 30.0), (212, 32.0), (212, 32.0), (213, 33.0), (214, 34.0),
+              (215, 35.0), (216, 36.0), (217, 37.0), (218, 38.0), (219, 39.0), (220, 40.0)]
+    assert order == expect
+
+
+def test_push_clean_when_ring_not_wrapped():
+    c = O.Cache(4, 32, 256)
+    for k, dd in [(1, 5.0), (2, 3.0), (3, 4.0), (2, 1.0), (4, 3.0)]:
+        c.push(k, dd)
+    keys, d, head, _ = c.state()
+    assert list(keys[:4]) == [4, 2, 3, 1] and list(d[:4]) == [3.0, 3.0, 4.0, 5.0]  # new goes before equal, dup key dropped
+    assert list(keys[4:8]) == [4, 2, 3, 1]
+
+
+@pytest.mark.parametrize("name", ["l2_10k", "cos_10k"])
+def test_oracle_query_matches_reference_dump(golden, name):
+    g = golden[name]
+    cfg = O.graph_config(g["N"], g["D"], g["kbuild"])
+    gr = O.Graph(cfg, g["blob"])
+    n = 400
+    ids, dists = O.query(g["base"], g["query"][:n], gr.layer_graph(0), gr.start_points(), gr.nn1_stats, g["kquery"],
+                         g["tau_query"], g["max_it"], g["measure"])
+    assert np.array_equal(ids, g["query_ids"][:n])
+    assert np.array_equal(dists, g["query_dists"][:n])
+
+
+@pytest.mark.parametrize("name", ["l2_10k", "cos_10k"])
+def test_oracle_bf_matches_reference_dump(golden, name):
+    g = golden[name]
+    n = 48
+    ids, dists = O.bf_query(g["base"], g["query"][:n], g["kquery"], g["measure"])
+    assert np.array_equal(ids, g["bf_ids"][:n])
+    assert np.array_equal(dists, g["bf_dists"][:n])
+
+
+@pytest.mark.parametrize("name", ["l2_10k", "cos_10k"])
+def test_oracle_top_and_select_reproduce_reference_graph(golden, name):
+    """Deterministic construction stages: the top-layer segment kNN (`top`) of layer 3 depends only on
+    translation[3]; the reference's sym pass then only rewrites the foreign half.  The local half
+    (first KL columns) of graph[3] must match the oracle's `top` bit for bit."""
+    g = golden[name]
+    cfg = O.graph_config(g["N"], g["D"], g["kbuild"])
+    ref = O.Graph(cfg, g["blob"])
+    mine = O.Graph(cfg, g["blob"].copy())
+    mine.layer_graph(3)[:] = -7
+    O.top(mine, g["base"], 3, g["measure"])
+    KL = cfg.KBuild - cfg.KBuild // 2
+    assert np.array_equal(mine.layer_graph(3)[:, :KL], ref.layer_graph(3)[:, :KL])
+
+
+def test_oracle_eval_matches_definition():
+    rng = np.random.default_rng(0)
+    gt = np.stack([rng.permutation(1000)[:20] for _ in range(50)]).astype(np.int32)
+    res = gt[:, :10].copy()
+    res[:, 5:] = 5000 + np.arange(5)  # 5 of 10 correct
+    res[::2, 0] = 7777                # top-1 wrong for every second query
+    e = O.evaluate(gt, res, 10)
+    assert e["cK"] == pytest.approx((50 * 5 - 25) / 500)
+    assert e["c1"] == pytest.approx(0.5) and e["rK"] == pytest.approx(0.5)
