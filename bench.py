@@ -32,16 +32,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEF = dict(n_base=1_000_000, n_query=10_000, dim=128, k_build=24, tau_build=0.5, refine=2, k_query=10,
-           tau_query=0.64, max_iterations=400, kind="clustered", seed=1234)
+           tau_query=0.64, max_iterations=400, kind="manifold16", seed=1234)
 
 
 def gen_gpu(N, Nq, D, kind, seed, device, shard_index=0):
-    """synthetic SIFT1M-shape data generated on the device (fp32).  'clustered': mixture of 1000 Gaussians,
-    clipped to [0,255] and rounded (integers stored as fp32, like SIFT); 'uniform': U[0,1)."""
+    """synthetic SIFT1M-shape data generated on the device (fp32, no dataset files offline).
+    'manifold<d>' (default manifold16): SIFT-like -- points on a d-dimensional linear manifold embedded in D dims
+                  (low intrinsic dimension like real descriptors), per-dim std 40 around 128, unit Gaussian noise,
+                  clipped to [0,255] and rounded: integer-valued vectors stored as fp32, like SIFT.
+    'uniform'   : U[0,1) in every dim (the reference's README example; intrinsic dimension = D, a very hard ANN
+                  instance: neither the reference nor this implementation gets useful recall at 1M points).
+    'clustered' : mixture of 1000 isotropic Gaussians (intrinsic dimension = D, equally hard).
+    Queries are drawn from the same distribution with a separate generator; shards differ by `shard_index`."""
     g = torch.Generator(device=device).manual_seed(seed)
+    gb = torch.Generator(device=device).manual_seed(seed + 17 * (shard_index + 1))
     if kind == "uniform":
-        gb = torch.Generator(device=device).manual_seed(seed + 17 * (shard_index + 1))
         return torch.rand((N, D), generator=gb, device=device), torch.rand((Nq, D), generator=g, device=device)
+    if kind.startswith("manifold"):
+        d = int(kind[len("manifold"):] or 16)
+        A = torch.randn((d, D), generator=g, device=device) / (d ** 0.5)
+
+        def draw(n, gen):
+            out = torch.empty((n, D), device=device)
+            for lo in range(0, n, 1 << 20):  # chunked to bound temporaries
+                m = min(1 << 20, n - lo)
+                z = torch.randn((m, d), generator=gen, device=device)
+                x = (z @ A) * 40.0 + 128.0 + torch.randn((m, D), generator=gen, device=device)
+                out[lo:lo + m] = x.round_().clamp_(0, 255)
+            return out
+        query = draw(Nq, g)
+        return draw(N, gb), query
     nc = 1000
     centers = torch.rand((nc, D), generator=g, device=device) * 160 + 20
 
@@ -50,7 +70,6 @@ def gen_gpu(N, Nq, D, kind, seed, device, shard_index=0):
         x = centers[c] + torch.randn((n, D), generator=gen, device=device) * 25
         return x.round_().clamp_(0, 255)
     query = draw(Nq, g)
-    gb = torch.Generator(device=device).manual_seed(seed + 17 * (shard_index + 1))
     return draw(N, gb), query
 
 

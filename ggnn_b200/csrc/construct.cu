@@ -936,13 +936,14 @@ extern "C" int ggnn_b200_top(const ggnn_b200_graph_config* cfg, const float* d_b
   a.translation = layer ? g.translation + cfg->STs_offsets[layer] : nullptr;
   a.graph = g.graph + static_cast<size_t>(cfg->Ns_offsets[layer]) * cfg->KBuild;
   a.nn1 = d_nn1;
-  const FastSel f = fast_sel(a.D, a.VB, a.items);
+  FastSel f = fast_sel(a.D, a.VB, a.items);
+  const int NSK = (a.KBuild + 31) / 32;
+  f.fast = f.fast && f.nw == 4 && NSK <= 2;
   if (int rc = make_plan(a.pl, a.D, !f.fast, false, 0, 0, 0, 16)) return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
-  const int NSK = (a.KBuild + 31) / 32;
 #define G200_TOP(NSK_, FAST_, D32_, NW_) \
   return launch_warp_kernel(top_kernel<NSK_, FAST_, D32_, NW_>, a, a.N_layer, smem, stream, "top_kernel")
-  if (f.fast && f.nw == 4) {
+  if (f.fast) {
     switch (NSK * 10 + f.d32) {
       case 11: G200_TOP(1, true, 1, 4);
       case 12: G200_TOP(1, true, 2, 4);
@@ -1039,14 +1040,15 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
   a.max_iterations = 200;
   a.sorted = std::max(64u, next_multiple32(cfg->KBuild + 1 + 16));  // :64-65
   if (a.sorted >= a.cache) return set_error(GGNN_B200_ERR_INVALID, "SORTED_SIZE >= CACHE_SIZE");
-  const FastSel f = fast_sel(a.D, a.VB, a.items);
+  FastSel f = fast_sel(a.D, a.VB, a.items);
+  const int NS = a.sorted / 32;
+  f.fast = f.fast && f.nw == 1 && NS == 2;  // the register-resident variants that are instantiated
   if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, 16)) return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
-  const int NS = a.sorted / 32;
   int rc = -1;
 #define G200_MERGE(NS_, FAST_, D32_, NW_) \
   rc = launch_warp_kernel(merge_kernel<NS_, FAST_, D32_, NW_>, a, a.N_btm, smem, stream, "merge_kernel")
-  if (f.fast && f.nw == 1 && NS == 2) {
+  if (f.fast) {
     switch (f.d32) {
       case 1: G200_MERGE(2, true, 1, 1); break;
       case 2: G200_MERGE(2, true, 2, 1); break;
@@ -1103,13 +1105,14 @@ extern "C" int ggnn_b200_sym(const ggnn_b200_graph_config* cfg, const float* d_b
   if (e != cudaSuccess) return set_cuda_error(e, "memset sym_buffer");
   e = cudaMemsetAsync(d_sym_atomic, 0, static_cast<size_t>(a.N_layer) * sizeof(uint32_t), stream);
   if (e != cudaSuccess) return set_cuda_error(e, "memset sym_atomic");
-  const FastSel f = fast_sel(a.D, a.VB, a.items);
+  FastSel f = fast_sel(a.D, a.VB, a.items);
+  const int NS = a.sorted / 32;
+  f.fast = f.fast && f.nw == 2 && NS == 2;
   if (int rc = make_plan(a.pl, a.D, !f.fast, !f.fast, a.sorted, a.cache, a.max_iterations, 16)) return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
-  const int NS = a.sorted / 32;
 #define G200_SYM(NS_, FAST_, D32_, NW_) \
   return launch_warp_kernel(sym_kernel<NS_, FAST_, D32_, NW_>, a, a.N_layer, smem, stream, "sym_kernel")
-  if (f.fast && f.nw == 2 && NS == 2) {
+  if (f.fast) {
     switch (f.d32) {
       case 1: G200_SYM(2, true, 1, 2);
       case 2: G200_SYM(2, true, 2, 2);

@@ -187,7 +187,8 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(work counter)");
   }
 
-  const bool fast = (p.block_dim_x == 32) && (p.D % 32 == 0) && (p.D <= 128);
+  // the FAST variants (query vector in registers) exist for NS <= 2; everything else takes the generic kernel
+  const bool fast = (p.block_dim_x == 32) && (p.D % 32 == 0) && (p.D <= 128) && (NS <= 2);
   const int NI = p.D / 32;
 
   // per-warp shared memory plan
