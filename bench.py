@@ -32,12 +32,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEF = dict(n_base=1_000_000, n_query=10_000, dim=128, k_build=24, tau_build=0.5, refine=2, k_query=10,
-           tau_query=0.64, max_iterations=400, kind="manifold16", seed=1234)
+           tau_query=0.64, max_iterations=400, kind="manifold8", seed=1234)
 
 
 def gen_gpu(N, Nq, D, kind, seed, device, shard_index=0):
     """synthetic SIFT1M-shape data generated on the device (fp32, no dataset files offline).
-    'manifold<d>' (default manifold16): SIFT-like -- points on a d-dimensional linear manifold embedded in D dims
+    'manifold<d>' (default manifold8: at the reference's documented SIFT1M operating point tau_query=0.64,
+                  max_iterations=400 it reaches the documented recall@10 of 0.99, measured for both implementations): SIFT-like -- points on a d-dimensional linear manifold embedded in D dims
                   (low intrinsic dimension like real descriptors), per-dim std 40 around 128, unit Gaussian noise,
                   clipped to [0,255] and rounded: integer-valued vectors stored as fp32, like SIFT.
     'uniform'   : U[0,1) in every dim (the reference's README example; intrinsic dimension = D, a very hard ANN

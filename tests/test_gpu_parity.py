@@ -216,7 +216,8 @@ def test_construction_kernels_bit_exact_vs_oracle(D, measure, kind, N):
             rng_off += cfg_o.Ns[layer]
             O.select(ref, layer, nn1_o, r)
             sync_nn1 = dev(np.pad(nn1_o, (0, N - nn1_o.size)))
-            _lib.check(lib.ggnn_b200_select(C.byref(dg.cfg), layer, ptr(sync_nn1), ptr(dev(r)), ptr(dg.blob), stream()))
+            r_d = dev(r)
+            _lib.check(lib.ggnn_b200_select(C.byref(dg.cfg), layer, ptr(sync_nn1), ptr(r_d), ptr(dg.blob), stream()))
             torch.cuda.synchronize()
             got = dg.host(cfg_o)
             assert np.array_equal(got.layer_selection(layer + 1), ref.layer_selection(layer + 1)), f"select {layer}"
@@ -225,8 +226,8 @@ def test_construction_kernels_bit_exact_vs_oracle(D, measure, kind, N):
         # --- sym_buffer_merge on the oracle's (sequential) sym result ---
         sb, sa = O.sym(ref, base, layer, tau, measure)
         O.sym_buffer_merge(ref, layer, sb, sa)
-        _lib.check(lib.ggnn_b200_sym_buffer_merge(C.byref(dg.cfg), layer, ptr(dev(sb)), ptr(dev(sa.astype(np.int32))),
-                                                  ptr(dg.blob), stream()))
+        sb_d, sa_d = dev(sb), dev(sa.astype(np.int32))  # keep the device copies alive until the kernel ran
+        _lib.check(lib.ggnn_b200_sym_buffer_merge(C.byref(dg.cfg), layer, ptr(sb_d), ptr(sa_d), ptr(dg.blob), stream()))
         torch.cuda.synchronize()
         assert np.array_equal(dg.host(cfg_o).layer_graph(layer), ref.layer_graph(layer)), f"sym_buffer_merge {layer}"
         # --- merges from this top layer down ---
@@ -253,13 +254,14 @@ def test_sym_kernel_matches_oracle_where_the_race_cannot_matter(D, measure, kind
     ref = O.build_graph(cfg_o, base, tau, rng, 0, measure)  # a complete graph to run sym on
     lib = _lib.lib()
     dg = DevGraph(cfg_o, ref.blob)
+    b_d = dev(base)
     KF = K // 2
     for layer in (0, 1):
         Nl = cfg_o.Ns[layer]
         sb_o, sa_o = O.sym(ref, base, layer, tau, measure)
         sb = torch.zeros((Nl, KF), dtype=torch.int32, device="cuda")
         sa = torch.zeros(Nl, dtype=torch.int32, device="cuda")
-        _lib.check(lib.ggnn_b200_sym(C.byref(dg.cfg), ptr(dev(base)), measure, tau, layer, ptr(dg.blob), ptr(sb), ptr(sa), stream()))
+        _lib.check(lib.ggnn_b200_sym(C.byref(dg.cfg), ptr(b_d), measure, tau, layer, ptr(dg.blob), ptr(sb), ptr(sa), stream()))
         torch.cuda.synchronize()
         sb, sa = sb.cpu().numpy(), sa.cpu().numpy().astype(np.int64)
         # invariants: counts match the number of filled slots (capped at KF); requested links are valid ids
@@ -318,9 +320,8 @@ def test_store_load_roundtrip_is_byte_compatible(tmp_path, golden):
 @pytest.fixture(scope="module")
 def big():
     N, Nq, D = 1_000_000, 10_000, 128
-    g = torch.Generator(device="cuda").manual_seed(1234)
-    base = torch.rand((N, D), generator=g, device="cuda")
-    query = torch.rand((Nq, D), generator=g, device="cuda")
+    import bench
+    base, query = bench.gen_gpu(N, Nq, D, bench.DEF["kind"], 1234, torch.device("cuda", 0))  # bench.py's workload
     idx = ggnn.GGNN()
     idx.set_return_results_on_gpu(True)
     idx.set_base(base)
@@ -345,7 +346,7 @@ def test_full_size_properties(big):
     assert bool((gtd[:, 1:] >= gtd[:, :-1]).all())
     assert bool((gtd <= dists[:2000]).all())
     rec = ggnn.Evaluator(None, None, gt, K).evaluate_results(ids[:2000]).c_k_query
-    assert rec > 0.5, rec  # uniform 128-d data is a hard ANN instance; the exact figure is reported by bench.py
+    assert rec >= 0.985, rec  # BASELINE config 2 operating point (tau 0.64, 400 iterations); bench.py reports the figure
     # self-queries: a base point finds itself at distance 0
     sids, sd = idx.query(base[:1000].contiguous(), 1, 0.64, 400)
     assert float((sids[:, 0] == torch.arange(1000, device="cuda", dtype=torch.int32)).float().mean()) > 0.99
