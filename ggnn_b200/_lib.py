@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libggnn_b200.so")
+LIB_PATH = os.environ.get("GGNN_B200_LIB") or os.path.join(_HERE, "libggnn_b200.so")
 
 EUCLIDEAN, COSINE = 0, 1
 L = 4

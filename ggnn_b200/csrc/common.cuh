@@ -69,6 +69,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (SASS: LDGSTS.E.BYPASS.128), one warp instruction moves a
+// whole 512-byte row; used as the alternative row-staging mode (see traverse.cuh)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // reference-order reductions
 // ------------------------------------------------------------------------------------------------

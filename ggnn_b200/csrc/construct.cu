@@ -36,7 +36,7 @@ static GraphPtrs graph_ptrs(const ggnn_b200_graph_config& c, void* blob)
 
 // per-warp shared memory plan shared by top / merge / sym
 struct WarpPlan {
-  uint32_t warp_smem_bytes, stage_rows, hsize, ring_cap;
+  uint32_t warp_smem_bytes, stage_rows, hsize, ring_cap, stage_mode;
   uint32_t off_sq, off_half, off_sorted, off_hash, off_ring, off_bar;
 };
 static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uint32_t sorted, uint32_t cache,
@@ -52,7 +52,10 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / CW + 1)) / target_warps_per_sm;
   uint32_t rows = budget > fixed ? (budget - fixed) / row_bytes : 0;
   rows = std::max(8u, std::min(32u, rows / 8 * 8));
-  pl.stage_rows = rows;
+  pl.stage_rows = env_u32("GGNN_B200_BUILD_STAGE_ROWS", rows);
+  if (pl.stage_rows % 8 || pl.stage_rows == 0 || pl.stage_rows > 32) pl.stage_rows = rows;
+  rows = pl.stage_rows;
+  pl.stage_mode = env_u32("GGNN_B200_STAGE_MODE", 0);
   uint32_t off = align_up(rows * row_bytes, 16);
   pl.off_sq = off;
   off += need_sq ? align_up(row_bytes, 16) : 0;
@@ -81,6 +84,7 @@ __device__ __forceinline__ void init_warp_smem(WarpSmem& ws, VisitedSet& V, unsi
   ws.bar = reinterpret_cast<uint64_t*>(wbase + pl.off_bar);
   ws.parity = 0;
   ws.stage_rows = pl.stage_rows;
+  ws.stage_mode = pl.stage_mode;
   if (lane_id() == 0) mbar_init(ws.bar, 1);
   mbar_fence_init();
   __syncwarp();
@@ -633,13 +637,8 @@ __device__ __forceinline__ void sym_stage_and_dist(WarpSmem& ws, const SymVec<FA
 {
   const int lane = lane_id();
   const uint32_t D = sv.cfg.D;
-  const uint32_t row_bytes = D * 4u;
-  if (lane == 0) mbar_expect_tx(ws.bar, row_bytes * nb);
-  __syncwarp();
   const int r = lane - b0;
-  if (r >= 0 && r < nb) bulk_g2s(ws.stage + static_cast<size_t>(r) * D, base + static_cast<size_t>(m) * D, row_bytes, ws.bar);
-  mbar_wait(ws.bar, ws.parity);
-  ws.parity ^= 1;
+  stage_rows_g2s(ws, base, D, m, b0, nb);
   if constexpr (FAST) {
     for (int g = 0; g * 8 < nb; ++g) {
       float dq, dh;
@@ -798,8 +797,10 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const SymArgs a)
         const unsigned mask = __ballot_sync(FULL, valid);
         const int cnt = __popc(mask);
         if (!cnt) continue;
-        const unsigned src = __fns(mask, 0, lane + 1);
-        const int key_r = __shfl_sync(FULL, ck, src & 31);
+        __syncwarp();
+        if (valid) ws.s_sorted[__popc(mask & ((1u << lane) - 1u))] = ck;
+        __syncwarp();
+        const int key_r = ws.s_sorted[lane];
         int mm = 0;
         if (lane < cnt) mm = a.translation ? a.translation[key_r] : key_r;
         float mine_q = G200_INF, mine_h = G200_INF;

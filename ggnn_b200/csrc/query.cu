@@ -8,6 +8,10 @@
 #include <algorithm>
 #include <cstdlib>
 
+#ifndef G200_QUERY_MB
+#define G200_QUERY_MB 8  // min resident CTAs (4 warps each) per SM the register allocation must allow
+#endif
+
 namespace g200 {
 
 struct QueryArgs {
@@ -16,13 +20,15 @@ struct QueryArgs {
   uint32_t warps_per_cta;
   uint32_t warp_smem_bytes;
   uint32_t stage_rows;
+  uint32_t stage_mode;
+  uint32_t prefetch;   // 1: L2-prefetch the adjacency rows of promising candidates
   uint32_t hsize;      // visited hash slots (power of two)
   uint32_t ring_cap;   // 0 = ring mirror not needed
   uint32_t off_sq, off_sorted, off_hash, off_ring, off_bar;  // byte offsets in the per-warp block
 };
 
 template <int NS, bool FAST, int NI>
-__global__ void __launch_bounds__(256, 2) query_kernel(const QueryArgs a)
+__global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
@@ -37,6 +43,7 @@ __global__ void __launch_bounds__(256, 2) query_kernel(const QueryArgs a)
   ws.bar = reinterpret_cast<uint64_t*>(wbase + a.off_bar);
   ws.parity = 0;
   ws.stage_rows = a.stage_rows;
+  ws.stage_mode = a.stage_mode;
   if (lane == 0) mbar_init(ws.bar, 1);
   mbar_fence_init();
   __syncwarp();
@@ -73,7 +80,8 @@ __global__ void __launch_bounds__(256, 2) query_kernel(const QueryArgs a)
     // query_layer.cu:55 fetch_unfiltered(d_starting_points, nullptr, S)
     for (uint32_t i = 0; i < p.num_starting_points; i += 32) {
       const int ck = (i + lane < p.num_starting_points) ? p.d_starting_points[i + lane] : EMPTY_KEY;
-      fetch<NS, FAST, NI, 1, false>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st);
+      fetch<NS, FAST, NI, 1, false>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st, a.prefetch ? p.d_graph : nullptr,
+                                    p.KBuild);
     }
 
     for (uint32_t ite = 0; ite < p.max_iterations; ++ite) {
@@ -91,7 +99,8 @@ __global__ void __launch_bounds__(256, 2) query_kernel(const QueryArgs a)
         const int ck = (i + lane < p.KBuild)
                            ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane)
                            : EMPTY_KEY;
-        fetch<NS, FAST, NI, 1, true>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st);
+        fetch<NS, FAST, NI, 1, true>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
+                                     p.KBuild);
       }
     }
 
@@ -199,8 +208,8 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   a.hsize = std::max(64u, 2u * bit_ceil_u32(std::max(1u, p.max_iterations)));
   const uint32_t fixed = (fast ? 0 : align_up(row_bytes, 16)) + p.sorted_size * 4 + a.hsize * 4 +
                          align_up(a.ring_cap * 4, 16) + 16;
-  a.warps_per_cta = env_u32("GGNN_B200_QUERY_WARPS", 4);
-  const uint32_t target_warps_per_sm = env_u32("GGNN_B200_QUERY_WARPS_PER_SM", 16);
+  a.warps_per_cta = std::min(4u, std::max(1u, env_u32("GGNN_B200_QUERY_WARPS", 4)));
+  const uint32_t target_warps_per_sm = env_u32("GGNN_B200_QUERY_WARPS_PER_SM", 24);
   const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / a.warps_per_cta + 1)) / target_warps_per_sm;
   uint32_t rows = budget > fixed ? (budget - fixed) / row_bytes : 0;
   rows = std::min(32u, rows / 8 * 8);
@@ -208,6 +217,8 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   rows = env_u32("GGNN_B200_QUERY_STAGE_ROWS", rows);
   if (rows % 8 || rows == 0 || rows > 32) return set_error(GGNN_B200_ERR_INVALID, "stage rows must be 8, 16, 24 or 32");
   a.stage_rows = rows;
+  a.stage_mode = env_u32("GGNN_B200_STAGE_MODE", 0);
+  a.prefetch = env_u32("GGNN_B200_QUERY_PREFETCH", 1);
   uint32_t off = align_up(rows * row_bytes, 16);
   a.off_sq = off;
   off += fast ? 0 : align_up(row_bytes, 16);

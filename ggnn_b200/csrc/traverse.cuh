@@ -16,7 +16,35 @@ struct WarpSmem {
   uint64_t* bar;     // mbarrier for the bulk copies
   uint32_t parity;   // phase of `bar`
   uint32_t stage_rows;  // multiple of 8
+  uint32_t stage_mode;  // 0: one cp.async.bulk (TMA engine) per row; 1: 16-byte cp.async per lane (LDGSTS)
 };
+
+// Move rows [b0, b0+nb) of the candidate list (lane b0+r holds the base row index m of local row r) into
+// the stage buffer and wait for them.  All rows are in flight together.
+__device__ __forceinline__ void stage_rows_g2s(WarpSmem& ws, const float* __restrict__ base, uint32_t D, int m, int b0, int nb)
+{
+  const int lane = lane_id();
+  const uint32_t row_bytes = D * 4u;
+  if (ws.stage_mode == 0) {
+    if (lane == 0) mbar_expect_tx(ws.bar, row_bytes * nb);
+    __syncwarp();
+    const int r = lane - b0;
+    if (r >= 0 && r < nb) bulk_g2s(ws.stage + static_cast<size_t>(r) * D, base + static_cast<size_t>(m) * D, row_bytes, ws.bar);
+    mbar_wait(ws.bar, ws.parity);
+    ws.parity ^= 1;
+  }
+  else {
+    const uint32_t chunks = row_bytes >> 4;
+    for (int r = 0; r < nb; ++r) {
+      const int mr = __shfl_sync(FULL, m, b0 + r);
+      const char* src = reinterpret_cast<const char*>(base + static_cast<size_t>(mr) * D);
+      char* dst = reinterpret_cast<char*>(ws.stage + static_cast<size_t>(r) * D);
+      for (uint32_t c = lane; c < chunks; c += 32) cp_async16(dst + c * 16, src + c * 16);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+  }
+}
 
 struct Stats {
   uint32_t pops, dists;
@@ -34,6 +62,26 @@ __device__ __forceinline__ float dist8_fast(const float* __restrict__ rows, int 
   constexpr int D = 32 * D32;
   if (measure == 0) {
     float v[NW][8];
+    if (nrows >= 8) {  // full group: straight-line code, no per-row branches
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float* rp = rows + i * D + lane;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          float acc = 0.f;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int c = it * NW + w;
+            if (c < D32) {
+              const float diff = rp[32 * c] - q[c];
+              acc = fmaf(diff, diff, acc);
+            }
+          }
+          v[w][i] = acc;
+        }
+      }
+    }
+    else
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -140,13 +188,8 @@ __device__ __forceinline__ float stage_and_dist(WarpSmem& ws, const QueryVec<FAS
 {
   const int lane = lane_id();
   const uint32_t D = qv.cfg.D;
-  const uint32_t row_bytes = D * 4u;
-  if (lane == 0) mbar_expect_tx(ws.bar, row_bytes * nb);
-  __syncwarp();
   const int r = lane - b0;
-  if (r >= 0 && r < nb) bulk_g2s(ws.stage + static_cast<size_t>(r) * D, base + static_cast<size_t>(m) * D, row_bytes, ws.bar);
-  mbar_wait(ws.bar, ws.parity);
-  ws.parity ^= 1;
+  stage_rows_g2s(ws, base, D, m, b0, nb);
 
   float mine = G200_INF;
   if constexpr (FAST) {
@@ -170,10 +213,14 @@ __device__ __forceinline__ float stage_and_dist(WarpSmem& ws, const QueryVec<FAS
 // One fetch of up to 32 candidate ids (ck per lane, EMPTY_KEY = none).
 //   FILTER  : drop ids present in best list / prioQ / visited set (simple_knn_cache.cuh:246-261)
 //   xi      : criteria() = dist[BEST-1] + xi, re-read after every push (:284)
+//   pf_graph/pf_stride: if non-null, the adjacency row of every candidate that passes the criteria at
+//             first sight (a likely future anchor) is prefetched into L2 -- the pop -> adjacency load is the
+//             serial latency chain of the traversal and DRAM bandwidth is plentiful
 template <int NS, bool FAST, int D32, int NW, bool FILTER>
 __device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, WarpSmem& ws,
                                       const QueryVec<FAST, D32, NW>& qv, const float* __restrict__ base,
-                                      const int* __restrict__ translation, int ck, float xi, Stats& st)
+                                      const int* __restrict__ translation, int ck, float xi, Stats& st,
+                                      const int* __restrict__ pf_graph = nullptr, uint32_t pf_stride = 0)
 {
   const int lane = lane_id();
   bool valid = ck != EMPTY_KEY;
@@ -188,9 +235,12 @@ __device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, War
   if (cnt == 0) return;
   st.dists += cnt;
 
-  // compact: lane r <- r-th surviving candidate (adjacency order preserved)
-  const unsigned src = __fns(mask, 0, lane + 1);
-  const int key_r = __shfl_sync(FULL, ck, src & 31);
+  // compact: lane r <- r-th surviving candidate (adjacency order preserved), through shared memory
+  // (the sorted-key mirror is free again after the filter; __fns would be a ~50-instruction software loop)
+  __syncwarp();
+  if (valid) ws.s_sorted[__popc(mask & ((1u << lane) - 1u))] = ck;
+  __syncwarp();
+  const int key_r = ws.s_sorted[lane];
   int m = 0;
   if (lane < cnt) m = translation ? translation[key_r] : key_r;
 
@@ -199,6 +249,15 @@ __device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, War
     const int nb = min(static_cast<int>(ws.stage_rows), cnt - b0);
     const float d = stage_and_dist<FAST, D32, NW>(ws, qv, base, m, b0, nb);
     if (lane >= b0 && lane < b0 + nb) mine = d;
+  }
+
+  if (pf_graph) {
+    const float crit0 = L.dist_at(L.BEST - 1) + xi;
+    if (lane < cnt && mine < crit0) {
+      const int* row = pf_graph + static_cast<size_t>(key_r) * pf_stride;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + pf_stride - 1));
+    }
   }
 
   // pushes in candidate order; criteria re-evaluated after each push

@@ -1,4 +1,5 @@
-"""Launch-parameter exploration for the traversal kernel on the GPU box (build once, time many settings)."""
+"""Launch-parameter exploration for the traversal kernel on the GPU box (build once, time many settings).
+usage: [GGNN_B200_LIB=...] python tools/tune_query.py kinds rows_list modes_list tag"""
 import itertools
 import json
 import os
@@ -14,6 +15,9 @@ import ggnn_b200 as ggnn  # noqa: E402
 
 def main():
     kinds = sys.argv[1].split(",") if len(sys.argv) > 1 else ["manifold8", "manifold16"]
+    rows_l = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "8,16,24").split(",")]
+    modes = [int(x) for x in (sys.argv[3] if len(sys.argv) > 3 else "0,1").split(",")]
+    tag = sys.argv[4] if len(sys.argv) > 4 else "default"
     dev = torch.device("cuda", 0)
     res = []
     for kind in kinds:
@@ -23,9 +27,9 @@ def main():
         idx.set_base(base)
         idx.build(24, 0.5, 2)
         ref_ids = None
-        for warps, wpsm, rows in itertools.product((2, 4, 8), (8, 12, 16, 24, 32), (8, 16, 24)):
-            os.environ["GGNN_B200_QUERY_WARPS"] = str(warps)
-            os.environ["GGNN_B200_QUERY_WARPS_PER_SM"] = str(wpsm)
+        for pf, mode, rows in itertools.product((0, 1), modes, rows_l):
+            os.environ["GGNN_B200_QUERY_PREFETCH"] = str(pf)
+            os.environ["GGNN_B200_STAGE_MODE"] = str(mode)
             os.environ["GGNN_B200_QUERY_STAGE_ROWS"] = str(rows)
             try:
                 idx.query(query, 10, 0.64, 400)
@@ -42,11 +46,13 @@ def main():
                 same = bool(torch.equal(ids, ref_ids))
             except Exception as e:
                 ms, same = None, str(e)[:80]
-            res.append({"kind": kind, "warps_per_cta": warps, "warps_per_sm_target": wpsm, "stage_rows": rows, "ms": ms, "same": same})
+            res.append({"tag": tag, "kind": kind, "prefetch": pf, "stage_mode": mode, "stage_rows": rows, "ms": ms, "same": same})
             print(res[-1], flush=True)
         del idx, base, query
         torch.cuda.empty_cache()
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "tune_query.json"), "w"), indent=1)
+    with open(os.path.join(ROOT, "gpurun_out", "tune_query.jsonl"), "a") as f:
+        for r in res:
+            f.write(json.dumps(r) + "\n")
 
 
 if __name__ == "__main__":
