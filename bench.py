@@ -75,41 +75,54 @@ def gen_gpu(N, Nq, D, kind, seed, device, shard_index=0):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """samples SM clock and clock-event (throttle) reasons of one GPU DURING the timed region: NVML polled every
+    ~2 ms from a thread (nvidia-smi -lms is too coarse for a millisecond-scale region)."""
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.sm, self.reasons, self.stop_flag, self.t, self.err = gpu, [], set(), False, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=1.0)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def measured_peaks():
@@ -195,9 +208,9 @@ def run_ours(a):
     # (n_dist already includes the S start-point evaluations)
 
     # ---- timed region 1: device-resident ----
+    sampler = ClockSampler(local)
     for _ in range(a.warmup):
         step_device()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     if world > 1:
@@ -300,18 +313,23 @@ def cpu_baseline(a, idx, base, query, gr):
     """CPU oracle port of the same traversal (same graph), all host cores, bounded query sample (~10-30 s)."""
     from oracle import pyoracle as O
     cores = os.cpu_count() or 1
-    n = min(a.n_query, max(64, 40 * cores))
+    O.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1
+    torch.set_num_threads(cores)
+    n = a.n_query
     b = base.cpu().numpy()
     q = query[:n].cpu().numpy()
     g0 = gr.layer_graph(0).cpu().numpy()
     sp = gr.layer_translation(3).cpu().numpy()
     ns = gr.nn1_stats.cpu().numpy()
-    O.query(b, q[:8], g0, sp, ns, a.k_query, a.tau_query, a.max_iterations)  # warm
+    O.query(b, q[:cores], g0, sp, ns, a.k_query, a.tau_query, a.max_iterations)  # warm
     t0 = time.perf_counter()
-    O.query(b, q, g0, sp, ns, a.k_query, a.tau_query, a.max_iterations)
+    reps = 0
+    while reps < 200 and time.perf_counter() - t0 < 10.0:  # bounded sample: ~10 s of CPU work
+        O.query(b, q, g0, sp, ns, a.k_query, a.tau_query, a.max_iterations)
+        reps += 1
     dt = time.perf_counter() - t0
-    out = {"value": n / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-           "sample": f"{n} of {a.n_query} queries, same graph and parameters, OpenMP over queries ({dt:.2f} s)"}
+    out = {"value": n * reps / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+           "sample": f"all {n} queries x {reps} passes, same graph and parameters, OpenMP over queries ({dt:.2f} s)"}
     # exact brute force on the host cores (torch CPU SGEMM formulation), for context
     try:
         nb = min(n, 256)
@@ -354,7 +372,7 @@ def run_reference(a):
     reps = a.warmup + a.steps
     args = [drv, f"dir={wd}", f"n={a.n_base * shards}", f"nq={a.n_query}", f"d={a.dim}", "measure=0",
             f"kbuild={a.k_build}", f"tau_build={a.tau_build}", f"refine={a.refine}", "build=1", f"kquery={a.k_query}",
-            f"tau_query={a.tau_query}", f"max_iter={a.max_iterations}", f"query_reps={reps}", f"gpu_reps={reps}",
+            f"tau_query={a.tau_query}", f"max_iter={a.max_iterations}", f"query_reps={reps}", f"gpu_reps={reps if shards == 1 else 0}",
             f"bf={a.k_query if shards == 1 else 0}", "dump=1", f"gpus={shards}", f"shard={a.n_base}"]
     p = subprocess.run(args, capture_output=True, text=True)
     if p.returncode != 0:
@@ -362,7 +380,7 @@ def run_reference(a):
         return
     r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
     e2e = r["query_e2e_ms"][a.warmup:]
-    gpu = r["query_gpu_ms"][a.warmup:] if r.get("query_gpu_ms") else e2e
+    gpu = r["query_gpu_ms"][a.warmup:] if r.get("query_gpu_ms") else e2e  # N>1: the reference cannot keep results on the GPUs
     rec = None
     try:
         ids = np.fromfile(os.path.join(wd, "query_ids.bin"), np.int32).reshape(a.n_query, a.k_query)

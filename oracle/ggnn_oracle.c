@@ -16,10 +16,23 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define EMPTY_KEY (-1)
 #define EMPTY_DIST INFINITY
 #define K_BLOCK 32u
+
+/* number of OpenMP threads for the query-parallel loops (launchers like torchrun export OMP_NUM_THREADS=1) */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 static uint32_t bit_ceil_u32(uint32_t v) /* def.h:42-54 */
 {

@@ -60,6 +60,10 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    lib().orc_set_threads(C.c_int(int(n)))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

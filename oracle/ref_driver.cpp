@@ -181,7 +181,7 @@ int main(int argc, char** argv)
     printf("]");
   }
 
-  if (gpu_reps > 0) {
+  if (gpu_reps > 0 && getd(a, "gpus", 1) <= 1) {  // results on the GPU are single-GPU only (ggnn.cu:299-306)
     ggnn.setReturnResultsOnGPU(true);
     Dataset<float> q_gpu = Dataset<float>::emptyOnGPU(Nq, D, 0);
     query.copyTo(q_gpu);
