@@ -45,14 +45,14 @@ class BfQueryParams(C.Structure):
     _fields_ = [
         ("D", C.c_uint32), ("measure", C.c_int32), ("KQuery", C.c_uint32), ("N_base", C.c_int32),
         ("d_base", C.c_void_p), ("d_query", C.c_void_p), ("d_query_results", C.c_void_p),
-        ("d_query_results_dists", C.c_void_p),
+        ("d_query_results_dists", C.c_void_p), ("d_workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
 EXPORTS = [
     "ggnn_b200_last_error", "ggnn_b200_version", "ggnn_b200_graph_config_init", "ggnn_b200_graph_blob_bytes",
     "ggnn_b200_graph_blob_offsets", "ggnn_b200_build_scratch_bytes", "ggnn_b200_query_shape_init",
-    "ggnn_b200_query", "ggnn_b200_bf_query", "ggnn_b200_top", "ggnn_b200_nn1_stats", "ggnn_b200_select",
+    "ggnn_b200_query", "ggnn_b200_bf_query", "ggnn_b200_bf_query_workspace_bytes", "ggnn_b200_top", "ggnn_b200_nn1_stats", "ggnn_b200_select",
     "ggnn_b200_merge", "ggnn_b200_sym", "ggnn_b200_sym_buffer_merge", "ggnn_b200_build_graph",
     "ggnn_b200_merge_topk",
 ]
@@ -85,6 +85,8 @@ def lib():
         l.ggnn_b200_query_shape_init.argtypes = [C.POINTER(QueryShape), u32, u32, u32]
         l.ggnn_b200_query.argtypes = [C.POINTER(QueryParams), u32, vp]
         l.ggnn_b200_bf_query.argtypes = [C.POINTER(BfQueryParams), u32, vp]
+        l.ggnn_b200_bf_query_workspace_bytes.restype = C.c_size_t
+        l.ggnn_b200_bf_query_workspace_bytes.argtypes = [u32, i32, u32, u32, u32]
         l.ggnn_b200_top.argtypes = [cfgp, vp, i32, u32, vp, vp, vp]
         l.ggnn_b200_nn1_stats.argtypes = [vp, u32, vp, vp, vp]
         l.ggnn_b200_select.argtypes = [cfgp, u32, vp, vp, vp, vp]

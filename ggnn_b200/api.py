@@ -316,7 +316,13 @@ class GGNN:
             p.D, p.measure, p.KQuery, p.N_base = base.shape[1], int(measure), int(k_gt), base.shape[0]
             p.d_base, p.d_query = base.data_ptr(), q.data_ptr()
             p.d_query_results, p.d_query_results_dists = ids.data_ptr(), dists.data_ptr()
+            # scratch for the tensor-core contraction path (0 = shape not covered -> exact SIMT scan)
+            ws_bytes = l.ggnn_b200_bf_query_workspace_bytes(base.shape[1], int(measure), int(k_gt), base.shape[0], Nq)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+            p.d_workspace, p.workspace_bytes = (ws.data_ptr() if ws is not None else None), ws_bytes
             _lib.check(l.ggnn_b200_bf_query(C.byref(p), Nq, _stream_ptr(dev)))
+            if ws is not None:
+                ws.record_stream(torch.cuda.current_stream(dev))
         if self._results_on_gpu:
             return ids, dists
         return ids.cpu(), dists.cpu()

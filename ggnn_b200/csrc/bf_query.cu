@@ -15,6 +15,11 @@
 
 namespace g200 {
 
+// bf_tc.cu
+bool tc_supported(uint32_t D, uint32_t K, int measure);
+int tc_bf_query(const ggnn_b200_bf_query_params& p, uint32_t Nq, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D);
+
 constexpr int BF_WARPS = 8;
 constexpr int BF_QW = 4;  // queries per warp
 
@@ -262,6 +267,13 @@ static int launch_generic(const BfArgs& a, cudaStream_t stream)
 
 using namespace g200;
 
+extern "C" size_t ggnn_b200_bf_query_workspace_bytes(uint32_t D, int32_t measure, uint32_t KQuery, uint32_t N_base,
+                                                     uint32_t N_query)
+{
+  if (!tc_supported(D, KQuery, measure) || N_base < 128 || N_query == 0) return 0;
+  return tc_workspace_bytes(N_base, N_query, D);
+}
+
 extern "C" int ggnn_b200_bf_query(const ggnn_b200_bf_query_params* pin, uint32_t N_query, ggnn_b200_stream_t stream_)
 {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -277,6 +289,8 @@ extern "C" int ggnn_b200_bf_query(const ggnn_b200_bf_query_params* pin, uint32_t
   if (p.D == 0 || p.D > 4096) return set_error(GGNN_B200_ERR_INVALID, "D must be in [1, 4096]");
   if (p.N_base <= 0) return set_error(GGNN_B200_ERR_INVALID, "N_base must be positive");
   if (N_query == 0) return 0;
+  if (p.d_workspace && tc_supported(p.D, p.KQuery, p.measure) && p.N_base >= 128 && env_u32("GGNN_B200_BF_TC", 1))
+    return tc_bf_query(p, N_query, p.d_workspace, p.workspace_bytes, stream);
   a.N_query = N_query;
   a.block_dim_x = std::max(32u, bit_ceil_u32((p.D + 3) / 4));
   const int NSK = (p.KQuery + 31) / 32;

@@ -1,0 +1,601 @@
+// bf_tc.cu -- brute-force kNN as a dense tensor-core contraction (tcgen05 + TMEM + TMA), exact results.
+//
+// bf_query really is a contraction: ||b-q||^2 = ||b||^2 + (-2q).b + ||q||^2.  Three stages:
+//   1. split   : one streaming pass writes hi/lo TF32 halves of base and (-2)*query (x = hi + lo, hi = x with the
+//                13 low mantissa bits cleared) and the row norms.
+//   2. gemm    : persistent-over-N CTAs.  A = 128 query rows (hi, lo resident in shared memory), B = 128-row base
+//                tiles streamed by 2-D TMA (SWIZZLE_128B) through an mbarrier ring; one elected thread issues
+//                tcgen05.mma.kind::tf32 three times per k-step (hi*hi + hi*lo + lo*hi = "3xTF32", ~2^-21 relative)
+//                into a double-buffered 128x128 fp32 accumulator in TMEM; four epilogue warps read the accumulator
+//                with tcgen05.ld (one query row per thread), add ||b||^2 and keep, per row, the K best approximate
+//                scores seen so far; every base row whose score is within `margin` of the current K-th best is
+//                appended to the query's candidate list.  The margin bounds the approximation error of the score
+//                (see DESIGN.md), so the true top-K (in the reference's own fp32 arithmetic) is always a candidate.
+//   3. rerank  : one warp per query recomputes its few hundred candidates with the reference's exact fp32
+//                summation order (same code as the traversal kernels) and selects the K smallest (distance, index)
+//                pairs -- identical ids and distances to src/ggnn/query/bf_query_layer.cu:39-65.
+// A query whose candidate list overflows is re-done by the exact SIMT scan, so the result never depends on the
+// candidate capacity.
+#include "traverse.cuh"
+#include "host_util.h"
+#include "../../include/ggnn_b200.h"
+
+#include <cuda.h>
+
+#include <algorithm>
+
+namespace g200 {
+
+constexpr int TC_BM = 128;     // queries per CTA (UMMA M)
+constexpr int TC_BN = 128;     // base rows per tile (UMMA N)
+constexpr int TC_BK = 32;      // tf32 elements per shared-memory k-block (one 128-byte swizzle row)
+constexpr int TC_STAGES = 2;   // B ring depth (each stage = hi + lo k-block = 32 KB)
+constexpr int TC_KP = 32;      // max K of the tensor path (per-row best list in shared memory)
+constexpr int TC_THREADS = 256;
+constexpr uint32_t TC_KBLOCK_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr)
+{
+  // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused;
+  // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- stage 1: split + norms ---------------------------------------------------------------------
+// one warp per row; out rows padded with zeros up to n_rows_pad (TMA never reads past them anyway)
+__global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ x, uint32_t n_rows, uint32_t D, float scale,
+                                                       float* __restrict__ hi, float* __restrict__ lo,
+                                                       float* __restrict__ norms, unsigned int* __restrict__ max_norm_bits)
+{
+  const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = lane_id();
+  float acc = 0.f;
+  for (uint32_t d = lane; d < D; d += 32) {
+    const float v = x[static_cast<size_t>(row) * D + d];
+    acc = fmaf(v, v, acc);
+    const float s = v * scale;  // scale is a power of two: exact
+    const float h = __uint_as_float(__float_as_uint(s) & 0xffffe000u);
+    hi[static_cast<size_t>(row) * D + d] = h;
+    lo[static_cast<size_t>(row) * D + d] = s - h;  // exact
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  if (lane == 0) {
+    norms[row] = acc;
+    if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(acc));  // non-negative floats order like uints
+  }
+}
+
+// ---- stage 2: the contraction -------------------------------------------------------------------
+struct TcGemmArgs {
+  uint32_t N_base, N_query, K, cap;
+  uint32_t rows_per_split;  // multiple of TC_BN
+  const float* bnorm;       // [N_base]
+  const float* qnorm;       // [N_query]
+  const unsigned int* max_norm_bits;
+  int32_t* cand;            // [N_query, cap]
+  uint32_t* cnt;            // [N_query]
+};
+
+template <int KB>  // k-blocks: D = 32*KB
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const TcGemmArgs a)
+{
+  extern __shared__ unsigned char smem_unaligned[];
+  // carve-up (every operand tile 1024-byte aligned: required by the 128-byte swizzle)
+  unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  unsigned char* sA_hi = smem;                                  // [KB][16 KB]
+  unsigned char* sA_lo = sA_hi + KB * TC_KBLOCK_BYTES;          // [KB][16 KB]
+  unsigned char* sB = sA_lo + KB * TC_KBLOCK_BYTES;             // [STAGES][hi 16 KB | lo 16 KB]
+  float* s_kbest = reinterpret_cast<float*>(sB + TC_STAGES * 2 * TC_KBLOCK_BYTES);  // [128][TC_KP]
+  float* s_bnorm = s_kbest + TC_BM * TC_KP;                     // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bnorm + 2 * TC_BN);
+  uint64_t* full = bars;                    // [STAGES]
+  uint64_t* empty = bars + TC_STAGES;       // [STAGES]
+  uint64_t* a_full = bars + 2 * TC_STAGES;  // [1]
+  uint64_t* t_full = a_full + 1;            // [2]
+  uint64_t* t_empty = t_full + 2;           // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = lane_id();
+  const uint32_t q0 = blockIdx.x * TC_BM;
+  const uint32_t n_begin = blockIdx.y * a.rows_per_split;
+  const uint32_t n_end = min(a.N_base, n_begin + a.rows_per_split);
+  const uint32_t n_tiles = (n_end > n_begin) ? (n_end - n_begin + TC_BN - 1) / TC_BN : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {  // TMEM: 2 accumulators x 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(a_full, 2 * KB * TC_KBLOCK_BYTES);
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_2d(sA_hi + kb * TC_KBLOCK_BYTES, &tm_qhi, a_full, kb * TC_BK, static_cast<int>(q0));
+        tma_load_2d(sA_lo + kb * TC_KBLOCK_BYTES, &tm_qlo, a_full, kb * TC_BK, static_cast<int>(q0));
+      }
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = 0; t < n_tiles; ++t) {
+        const int row = static_cast<int>(n_begin + t * TC_BN);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], 2 * TC_KBLOCK_BYTES);
+          unsigned char* dst = sB + stage * 2 * TC_KBLOCK_BYTES;
+          tma_load_2d(dst, &tm_bhi, &full[stage], kb * TC_BK, row);
+          tma_load_2d(dst + TC_KBLOCK_BYTES, &tm_blo, &full[stage], kb * TC_BK, row);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  }
+  else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32 (bit 4), A/B tf32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = 0; t < n_tiles; ++t) {
+        const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+        mbar_wait(&t_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * TC_BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da_hi = umma_desc_sw128(sA_hi + kb * TC_KBLOCK_BYTES);
+          const uint64_t da_lo = umma_desc_sw128(sA_lo + kb * TC_KBLOCK_BYTES);
+          const uint64_t db_hi = umma_desc_sw128(sB + stage * 2 * TC_KBLOCK_BYTES);
+          const uint64_t db_lo = umma_desc_sw128(sB + stage * 2 * TC_KBLOCK_BYTES + TC_KBLOCK_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = +2 in the descriptor's 16-byte units
+            const uint64_t ko = static_cast<uint64_t>(2 * k);
+            umma_tf32(tmem_c, da_hi + ko, db_hi + ko, idesc, (kb | k) != 0);
+            umma_tf32(tmem_c, da_hi + ko, db_lo + ko, idesc, 1);
+            umma_tf32(tmem_c, da_lo + ko, db_hi + ko, idesc, 1);
+          }
+          umma_commit(&empty[stage]);  // frees this B stage once the MMAs above have read it
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&t_full[acc]);  // accumulator complete
+      }
+    }
+  }
+  else if (warp >= 4) {
+    // ===== epilogue: one query row per thread =====
+    const int ew = warp - 4;                  // TMEM lane quarter == warp % 4
+    const uint32_t r = ew * 32 + lane;        // row in the tile
+    const uint32_t q = q0 + r;
+    const bool live = q < a.N_query;
+    const uint32_t K = a.K;
+    float* kb = s_kbest + r * TC_KP;
+    for (uint32_t i = 0; i < TC_KP; ++i) kb[i] = G200_INF;
+    // error bound of the approximate score: 2^-13 * (|q|^2 + max |b|^2)
+    const float margin = live ? ldexpf(a.qnorm[q] + __uint_as_float(*a.max_norm_bits), -13) : 0.f;
+    float tau = G200_INF;  // K-th best approximate score so far (+inf until K rows were seen)
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+      const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+      const uint32_t n0 = n_begin + t * TC_BN;
+      // stage the tile's base norms (rows past the end never qualify)
+      s_bnorm[acc * TC_BN + r] = (n0 + r < n_end) ? a.bnorm[n0 + r] : G200_INF;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&t_full[acc], acc_phase);
+      tc_fence_after();
+      const float4* bn4 = reinterpret_cast<const float4*>(s_bnorm + acc * TC_BN);
+#pragma unroll 1
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + acc * TC_BN + c * 32 + ((ew * 32u) << 16), v);
+        const float thr = tau + margin;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bn = bn4[c * 8 + j4];
+          const float s0 = v[4 * j4 + 0] + bn.x, s1 = v[4 * j4 + 1] + bn.y;
+          const float s2 = v[4 * j4 + 2] + bn.z, s3 = v[4 * j4 + 3] + bn.w;
+          if (fminf(fminf(s0, s1), fminf(s2, s3)) < thr) {  // rare after the first tiles
+            const float ss[4] = {s0, s1, s2, s3};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float s = ss[u];
+              if (s < tau + margin && live) {
+                const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
+                if (pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + pos] = static_cast<int32_t>(n0 + c * 32 + 4 * j4 + u);
+                if (s < tau) {  // insert into the row's sorted best list (ascending), K-th entry is tau
+                  int i = static_cast<int>(K) - 1;
+                  while (i > 0 && kb[i - 1] > s) {
+                    kb[i] = kb[i - 1];
+                    --i;
+                  }
+                  kb[i] = s;
+                  tau = kb[K - 1];
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ---- stage 3: exact re-rank ----------------------------------------------------------------------
+// sorted K-best by (dist, id) lexicographic order, insertion in any order
+template <int NSK>
+struct LexKBest {
+  int id[NSK];
+  float dist[NSK];
+  __device__ __forceinline__ void init()
+  {
+#pragma unroll
+    for (int j = 0; j < NSK; ++j) {
+      id[j] = 0x7fffffff;
+      dist[j] = G200_INF;
+    }
+  }
+  __device__ __forceinline__ static bool less(float d, int i, float d2, int i2) { return d < d2 || (d == d2 && i < i2); }
+  __device__ __forceinline__ void worst(uint32_t K, float& d, int& i) const
+  {
+    float v = dist[0];
+    int w = id[0];
+#pragma unroll
+    for (int j = 1; j < NSK; ++j) {
+      v = ((K - 1) >> 5) == j ? dist[j] : v;
+      w = ((K - 1) >> 5) == j ? id[j] : w;
+    }
+    d = __shfl_sync(FULL, v, (K - 1) & 31);
+    i = __shfl_sync(FULL, w, (K - 1) & 31);
+  }
+  __device__ __forceinline__ void add(float d, int i)
+  {
+    const int lane = lane_id();
+    int nid[NSK];
+    float nd[NSK];
+#pragma unroll
+    for (int j = 0; j < NSK; ++j) {
+      int pi = __shfl_up_sync(FULL, id[j], 1);
+      float pd = __shfl_up_sync(FULL, dist[j], 1);
+      if (j > 0) {
+        const int ci = __shfl_sync(FULL, id[j - 1], 31);
+        const float cd = __shfl_sync(FULL, dist[j - 1], 31);
+        if (lane == 0) {
+          pi = ci;
+          pd = cd;
+        }
+      }
+      const bool first = (j == 0 && lane == 0);
+      const bool shift_in = !first && less(d, i, pd, pi);
+      const bool ins = less(d, i, dist[j], id[j]) && (first || !less(d, i, pd, pi));
+      nid[j] = ins ? i : (shift_in ? pi : id[j]);
+      nd[j] = ins ? d : (shift_in ? pd : dist[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NSK; ++j) {
+      id[j] = nid[j];
+      dist[j] = nd[j];
+    }
+  }
+};
+
+struct TcRerankArgs {
+  ggnn_b200_bf_query_params p;
+  uint32_t N_query, cap, warp_smem_bytes;
+  const int32_t* cand;
+  const uint32_t* cnt;
+};
+
+template <int D32>
+__global__ void __launch_bounds__(128) tc_rerank_kernel(const TcRerankArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * 4 + warp;
+  if (n >= a.N_query) return;
+  const uint32_t cnt = a.cnt[n];
+  if (cnt > a.cap) return;  // overflow: handled by the exact scan (tc_fallback_kernel)
+  unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * a.warp_smem_bytes;
+  WarpSmem ws;
+  ws.stage = reinterpret_cast<float*>(wbase);
+  ws.s_q = nullptr;
+  ws.s_sorted = nullptr;
+  ws.bar = reinterpret_cast<uint64_t*>(wbase + 32 * D32 * 32 * 4);
+  ws.parity = 0;
+  ws.stage_rows = 32;
+  ws.stage_mode = 0;
+  if (lane == 0) mbar_init(ws.bar, 1);
+  mbar_fence_init();
+  __syncwarp();
+  const ggnn_b200_bf_query_params& p = a.p;
+  const DistCfg dc{p.D, 32u, 4u, 0};
+  QueryVec<true, D32, 1> qv;
+  qv.load(dc, p.d_query + static_cast<size_t>(n) * p.D, nullptr);
+  LexKBest<1> best;
+  best.init();
+  const uint32_t K = p.KQuery;
+  for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+    const int nb = min(32u, cnt - c0);
+    const int id = (lane < nb) ? a.cand[static_cast<size_t>(n) * a.cap + c0 + lane] : 0;
+    const float d = stage_and_dist<true, D32, 1>(ws, qv, p.d_base, id, 0, nb);
+    unsigned rem = nb >= 32 ? FULL : ((1u << nb) - 1u);
+    while (true) {
+      float wd;
+      int wi;
+      best.worst(K, wd, wi);
+      const unsigned pm = __ballot_sync(FULL, LexKBest<1>::less(d, id, wd, wi)) & rem;
+      if (!pm) break;
+      const int r = __ffs(pm) - 1;
+      best.add(__shfl_sync(FULL, d, r), __shfl_sync(FULL, id, r));
+      rem &= ~((2u << r) - 1u);
+    }
+  }
+  if (static_cast<uint32_t>(lane) < K) {
+    p.d_query_results[static_cast<size_t>(n) * K + lane] = best.id[0] == 0x7fffffff ? EMPTY_KEY : best.id[0];
+    if (p.d_query_results_dists) p.d_query_results_dists[static_cast<size_t>(n) * K + lane] = best.dist[0];
+  }
+}
+
+// exact scan for queries whose candidate list overflowed (same arithmetic as bf_query.cu's generic path)
+struct KBest1 {
+  int id;
+  float dist;
+};
+__global__ void __launch_bounds__(128) tc_fallback_kernel(const TcRerankArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * 4 + warp;
+  if (n >= a.N_query) return;
+  if (a.cnt[n] <= a.cap) return;
+  const ggnn_b200_bf_query_params& p = a.p;
+  float* s_q = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * p.D;
+  const DistCfg dc{p.D, 32u, 4u, 0};
+  QueryVec<false, 1, 1> qv;
+  qv.load(dc, p.d_query + static_cast<size_t>(n) * p.D, s_q);
+  LexKBest<1> best;
+  best.init();
+  const uint32_t K = p.KQuery;
+  for (int i = 0; i < p.N_base; ++i) {
+    float x, y;
+    dist_partials_generic(dc, p.d_base + static_cast<size_t>(i) * p.D, s_q, x, y);
+    float wd;
+    int wi;
+    best.worst(K, wd, wi);
+    if (LexKBest<1>::less(x, i, wd, wi)) best.add(x, i);
+  }
+  if (static_cast<uint32_t>(lane) < K) {
+    p.d_query_results[static_cast<size_t>(n) * K + lane] = best.id[0] == 0x7fffffff ? EMPTY_KEY : best.id[0];
+    if (p.d_query_results_dists) p.d_query_results_dists[static_cast<size_t>(n) * K + lane] = best.dist[0];
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// [rows, D] fp32 row-major, box = {32 floats (128 B), 128 rows}, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint32_t D)
+{
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(GGNN_B200_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  const cuuint64_t dims[2] = {D, rows};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 4};
+  const cuuint32_t box[2] = {TC_BK, TC_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(GGNN_B200_ERR_INVALID, "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+struct TcWorkspace {
+  float *b_hi, *b_lo, *bnorm, *q_hi, *q_lo, *qnorm;
+  unsigned int* max_norm;
+  uint32_t* cnt;
+  int32_t* cand;
+  size_t total;
+};
+static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, uint32_t cap)
+{
+  char* b = static_cast<char*>(basep);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = b + off;
+    off += (bytes + 1023) / 1024 * 1024;
+    return p;
+  };
+  TcWorkspace w;
+  w.b_hi = reinterpret_cast<float*>(take(static_cast<size_t>(N) * D * 4));
+  w.b_lo = reinterpret_cast<float*>(take(static_cast<size_t>(N) * D * 4));
+  w.bnorm = reinterpret_cast<float*>(take(static_cast<size_t>(N) * 4));
+  w.q_hi = reinterpret_cast<float*>(take(static_cast<size_t>(Nq) * D * 4));
+  w.q_lo = reinterpret_cast<float*>(take(static_cast<size_t>(Nq) * D * 4));
+  w.qnorm = reinterpret_cast<float*>(take(static_cast<size_t>(Nq) * 4));
+  w.max_norm = reinterpret_cast<unsigned int*>(take(1024));
+  w.cnt = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(Nq) * 4));
+  w.cand = reinterpret_cast<int32_t*>(take(static_cast<size_t>(Nq) * cap * 4));
+  w.total = off;
+  return w;
+}
+
+constexpr uint32_t TC_CAP = 1024;
+
+bool tc_supported(uint32_t D, uint32_t K, int measure)
+{
+  return measure == GGNN_B200_EUCLIDEAN && D % 32 == 0 && D >= 32 && D <= 128 && K >= 1 && K <= TC_KP;
+}
+
+template <int KB>
+static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorkspace& w, cudaStream_t stream)
+{
+  const uint32_t N = static_cast<uint32_t>(p.N_base), D = p.D;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(w.max_norm, 0, 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset max_norm");
+  if ((e = cudaMemsetAsync(w.cnt, 0, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset cnt");
+  tc_split_kernel<<<(N + 7) / 8, 256, 0, stream>>>(p.d_base, N, D, 1.0f, w.b_hi, w.b_lo, w.bnorm, w.max_norm);
+  tc_split_kernel<<<(Nq + 7) / 8, 256, 0, stream>>>(p.d_query, Nq, D, -2.0f, w.q_hi, w.q_lo, w.qnorm, nullptr);
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_split_kernel launch");
+
+  CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
+  if (int rc = make_map(&tq_hi, w.q_hi, Nq, D)) return rc;
+  if (int rc = make_map(&tq_lo, w.q_lo, Nq, D)) return rc;
+  if (int rc = make_map(&tb_hi, w.b_hi, N, D)) return rc;
+  if (int rc = make_map(&tb_lo, w.b_lo, N, D)) return rc;
+
+  const DeviceInfo& dev = device_info();
+  const uint32_t q_tiles = (Nq + TC_BM - 1) / TC_BM;
+  const uint32_t n_tiles = (N + TC_BN - 1) / TC_BN;
+  uint32_t splits = std::max(1u, std::min(n_tiles, (2 * dev.num_sms + q_tiles - 1) / q_tiles));
+  splits = env_u32("GGNN_B200_BF_SPLITS", splits);
+  const uint32_t tiles_per_split = (n_tiles + splits - 1) / splits;
+  splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+
+  TcGemmArgs ga{};
+  ga.N_base = N;
+  ga.N_query = Nq;
+  ga.K = p.KQuery;
+  ga.cap = TC_CAP;
+  ga.rows_per_split = tiles_per_split * TC_BN;
+  ga.bnorm = w.bnorm;
+  ga.qnorm = w.qnorm;
+  ga.max_norm_bits = w.max_norm;
+  ga.cand = w.cand;
+  ga.cnt = w.cnt;
+  const size_t smem = 2 * KB * TC_KBLOCK_BYTES + TC_STAGES * 2 * TC_KBLOCK_BYTES + TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
+  auto gemm = tc_gemm_kernel<KB>;
+  if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+    return set_cuda_error(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
+  gemm<<<dim3(q_tiles, splits), TC_THREADS, smem, stream>>>(tq_hi, tq_lo, tb_hi, tb_lo, ga);
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_gemm_kernel launch");
+
+  TcRerankArgs ra{};
+  ra.p = p;
+  ra.N_query = Nq;
+  ra.cap = TC_CAP;
+  ra.cand = w.cand;
+  ra.cnt = w.cnt;
+  ra.warp_smem_bytes = align_up(32 * D * 4 + 16, 128);
+  const size_t rsmem = static_cast<size_t>(ra.warp_smem_bytes) * 4;
+  auto rr = tc_rerank_kernel<KB>;
+  if ((e = cudaFuncSetAttribute(rr, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem))) != cudaSuccess)
+    return set_cuda_error(e, "cudaFuncSetAttribute(tc_rerank_kernel)");
+  rr<<<(Nq + 3) / 4, 128, rsmem, stream>>>(ra);
+  tc_fallback_kernel<<<(Nq + 3) / 4, 128, 4 * D * 4, stream>>>(ra);
+  return set_cuda_error(cudaGetLastError(), "tc_rerank / tc_fallback launch");
+}
+
+int tc_bf_query(const ggnn_b200_bf_query_params& p, uint32_t Nq, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+  const TcWorkspace w = tc_layout(workspace, static_cast<uint32_t>(p.N_base), Nq, p.D, TC_CAP);
+  if (workspace_bytes < w.total) return set_error(GGNN_B200_ERR_INVALID, "bf_query workspace too small");
+  switch (p.D / 32) {
+    case 1: return tc_run<1>(p, Nq, w, stream);
+    case 2: return tc_run<2>(p, Nq, w, stream);
+    case 3: return tc_run<3>(p, Nq, w, stream);
+    case 4: return tc_run<4>(p, Nq, w, stream);
+  }
+  return set_error(GGNN_B200_ERR_UNSUPPORTED, "tensor-core bf_query needs D in {32, 64, 96, 128}");
+}
+
+size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D) { return tc_layout(nullptr, N, Nq, D, TC_CAP).total; }
+
+}  // namespace g200

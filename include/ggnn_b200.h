@@ -116,7 +116,14 @@ typedef struct {
   const float* d_query;         /* [N_query, D] */
   int32_t* d_query_results;     /* [N_query, KQuery] */
   float* d_query_results_dists; /* [N_query, KQuery]; may be NULL */
+  void* d_workspace;            /* optional scratch of >= ggnn_b200_bf_query_workspace_bytes(): enables the
+                                   tensor-core path (tcgen05 3xTF32 contraction + exact re-rank, identical
+                                   results); NULL = exact SIMT scan */
+  size_t workspace_bytes;
 } ggnn_b200_bf_query_params;
+
+/* 0 if the tensor-core path does not apply to this shape (Euclidean, D in {32,64,96,128}, KQuery <= 32) */
+size_t ggnn_b200_bf_query_workspace_bytes(uint32_t D, int32_t measure, uint32_t KQuery, uint32_t N_base, uint32_t N_query);
 
 int ggnn_b200_bf_query(const ggnn_b200_bf_query_params* p, uint32_t N_query, ggnn_b200_stream_t stream);
 
