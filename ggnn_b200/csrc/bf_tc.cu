@@ -517,7 +517,39 @@ static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, u
   return w;
 }
 
-constexpr uint32_t TC_CAP = 1024;
+// Candidate capacity per query.  Every base split of a query emits roughly K*(1 + ln(rows/K)) candidates (its own
+// running K-th best starts at +inf), so the capacity bounds the number of splits; overflowing queries are re-done
+// exactly, the capacity only affects speed.
+constexpr uint32_t TC_CAP_MIN = 1024, TC_CAP_MAX = 8192, TC_CAND_PER_SPLIT = 192;
+
+static uint32_t tc_cap(uint32_t Nq)
+{
+  // keep the candidate buffer below ~256 MB
+  const uint64_t by_mem = (256ull << 20) / (static_cast<uint64_t>(std::max(1u, Nq)) * 4);
+  return static_cast<uint32_t>(std::max<uint64_t>(TC_CAP_MIN, std::min<uint64_t>(TC_CAP_MAX, by_mem)));
+}
+
+// number of base splits: fill the SMs (one 209 KB CTA each) in whole waves, within the candidate capacity
+static uint32_t tc_pick_splits(uint32_t q_tiles, uint32_t n_tiles, uint32_t num_sms, uint32_t cap)
+{
+  const uint32_t forced = env_u32("GGNN_B200_BF_SPLITS", 0);
+  const uint32_t s_max = std::max(1u, std::min(n_tiles, cap / TC_CAND_PER_SPLIT));
+  if (forced) return std::max(1u, std::min(forced, n_tiles));
+  uint32_t best = 1;
+  double best_score = -1.0;
+  for (uint32_t s = 1; s <= s_max; ++s) {
+    const uint64_t ctas = static_cast<uint64_t>(q_tiles) * s;
+    const uint64_t waves = (ctas + num_sms - 1) / num_sms;
+    const double eff = static_cast<double>(ctas) / static_cast<double>(waves * num_sms);
+    // prefer full waves; among equals, enough CTAs to cover the machine but as few splits as possible
+    const double score = eff - 0.002 * s;
+    if (score > best_score) {
+      best_score = score;
+      best = s;
+    }
+  }
+  return best;
+}
 
 bool tc_supported(uint32_t D, uint32_t K, int measure)
 {
@@ -528,6 +560,7 @@ template <int KB>
 static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorkspace& w, cudaStream_t stream)
 {
   const uint32_t N = static_cast<uint32_t>(p.N_base), D = p.D;
+  const uint32_t cap = tc_cap(Nq);
   cudaError_t e;
   if ((e = cudaMemsetAsync(w.max_norm, 0, 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset max_norm");
   if ((e = cudaMemsetAsync(w.cnt, 0, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset cnt");
@@ -544,16 +577,14 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   const DeviceInfo& dev = device_info();
   const uint32_t q_tiles = (Nq + TC_BM - 1) / TC_BM;
   const uint32_t n_tiles = (N + TC_BN - 1) / TC_BN;
-  uint32_t splits = std::max(1u, std::min(n_tiles, (2 * dev.num_sms + q_tiles - 1) / q_tiles));
-  splits = env_u32("GGNN_B200_BF_SPLITS", splits);
+  const uint32_t splits = tc_pick_splits(q_tiles, n_tiles, dev.num_sms, cap);
   const uint32_t tiles_per_split = (n_tiles + splits - 1) / splits;
-  splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
 
   TcGemmArgs ga{};
   ga.N_base = N;
   ga.N_query = Nq;
   ga.K = p.KQuery;
-  ga.cap = TC_CAP;
+  ga.cap = cap;
   ga.rows_per_split = tiles_per_split * TC_BN;
   ga.bnorm = w.bnorm;
   ga.qnorm = w.qnorm;
@@ -570,7 +601,7 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   TcRerankArgs ra{};
   ra.p = p;
   ra.N_query = Nq;
-  ra.cap = TC_CAP;
+  ra.cap = cap;
   ra.cand = w.cand;
   ra.cnt = w.cnt;
   ra.warp_smem_bytes = align_up(32 * D * 4 + 16, 128);
@@ -585,7 +616,7 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
 
 int tc_bf_query(const ggnn_b200_bf_query_params& p, uint32_t Nq, void* workspace, size_t workspace_bytes, cudaStream_t stream)
 {
-  const TcWorkspace w = tc_layout(workspace, static_cast<uint32_t>(p.N_base), Nq, p.D, TC_CAP);
+  const TcWorkspace w = tc_layout(workspace, static_cast<uint32_t>(p.N_base), Nq, p.D, tc_cap(Nq));
   if (workspace_bytes < w.total) return set_error(GGNN_B200_ERR_INVALID, "bf_query workspace too small");
   switch (p.D / 32) {
     case 1: return tc_run<1>(p, Nq, w, stream);
@@ -596,6 +627,6 @@ int tc_bf_query(const ggnn_b200_bf_query_params& p, uint32_t Nq, void* workspace
   return set_error(GGNN_B200_ERR_UNSUPPORTED, "tensor-core bf_query needs D in {32, 64, 96, 128}");
 }
 
-size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D) { return tc_layout(nullptr, N, Nq, D, TC_CAP).total; }
+size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D) { return tc_layout(nullptr, N, Nq, D, tc_cap(Nq)).total; }
 
 }  // namespace g200

@@ -30,6 +30,8 @@ def main():
              (1_000_000, 10_000, 128, 10, "manifold8"), (1_000_000, 10_000, 128, 10, "uniform")]
     if len(sys.argv) > 1:
         cases = cases[:int(sys.argv[1])]
+    if os.environ.get("BF_CASE"):
+        cases = [cases[int(os.environ["BF_CASE"])]]
     ok = True
     for N, Nq, D, K, kind in cases:
         base, query = bench.gen_gpu(N, Nq, D, kind, 7, dev)
