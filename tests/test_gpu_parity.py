@@ -55,7 +55,7 @@ def c_query(base, query, graph0, start, nn1_stats, K, tau, max_it, measure, spg=
     return out + (st.cpu().numpy().astype(np.uint32),) if stats else out
 
 
-def c_bf(base, query, K, measure):
+def c_bf(base, query, K, measure, tensor_cores=False):
     Nq, D = query.shape
     b, q = dev(base), dev(query)
     ids = torch.empty((Nq, K), dtype=torch.int32, device="cuda")
@@ -63,6 +63,12 @@ def c_bf(base, query, K, measure):
     p = _lib.BfQueryParams()
     p.D, p.measure, p.KQuery, p.N_base = D, measure, K, base.shape[0]
     p.d_base, p.d_query, p.d_query_results, p.d_query_results_dists = b.data_ptr(), q.data_ptr(), ids.data_ptr(), dists.data_ptr()
+    ws = None
+    if tensor_cores:  # tcgen05 3xTF32 contraction + exact re-rank (needs the scratch buffer)
+        nbytes = _lib.lib().ggnn_b200_bf_query_workspace_bytes(D, measure, K, base.shape[0], Nq)
+        assert nbytes > 0, "shape not covered by the tensor-core path"
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        p.d_workspace, p.workspace_bytes = ws.data_ptr(), nbytes
     _lib.check(_lib.lib().ggnn_b200_bf_query(C.byref(p), Nq, stream()))
     torch.cuda.synchronize()
     return ids.cpu().numpy(), dists.cpu().numpy()
@@ -89,6 +95,38 @@ def test_bf_query_matches_reference_dump(golden, name):
     g = golden[name]
     ids, dists = c_bf(g["base"], g["query"], g["kquery"], g["measure"])
     assert np.array_equal(ids, g["bf_ids"]) and np.array_equal(dists, g["bf_dists"])
+
+
+@pytest.mark.parametrize("N,Nq,D,K,kind", [(3000, 70, 128, 10, "uniform"), (1000, 300, 64, 32, "uniform"),
+                                           (2500, 129, 96, 1, "normal"), (333, 5, 32, 10, "uniform"),
+                                           (40000, 257, 128, 10, "uniform")])
+def test_bf_query_tensor_core_path_bit_exact_vs_oracle(N, Nq, D, K, kind):
+    """tcgen05 3xTF32 contraction -> candidate lists -> exact re-rank: same ids AND distances as the reference
+    arithmetic (oracle), including exact ties (duplicate rows) and ragged tile edges"""
+    base, query = gen_data(N, Nq, D, seed=N + D, kind=kind)
+    base[5] = base[3]
+    base[N - 1] = base[0]
+    query[0] = base[3]  # distance 0 twice
+    ids, dists = c_bf(base, query, K, 0, tensor_cores=True)
+    nq_o = min(Nq, 64)
+    o_ids, o_d = O.bf_query(base, query[:nq_o], K, 0)
+    assert np.array_equal(ids[:nq_o], o_ids) and np.array_equal(dists[:nq_o], o_d)
+    e_ids, e_d = c_bf(base, query, K, 0)  # all queries vs the exact SIMT scan
+    assert np.array_equal(ids, e_ids) and np.array_equal(dists, e_d)
+
+
+def test_bf_query_tensor_core_path_candidate_overflow_falls_back_exactly(golden):
+    """all base rows (nearly) equidistant: every row is a candidate, the lists overflow, the exact scan takes over"""
+    rng = np.random.default_rng(3)
+    base = np.tile(rng.random((1, 128), dtype=np.float32), (6000, 1))
+    base[::7] += 1e-3
+    query = rng.random((40, 128), dtype=np.float32)
+    ids, dists = c_bf(base, query, 10, 0, tensor_cores=True)
+    e_ids, e_d = c_bf(base, query, 10, 0)
+    assert np.array_equal(ids, e_ids) and np.array_equal(dists, e_d)
+    g = golden["l2_10k"]
+    ids, dists = c_bf(g["base"], g["query"], g["kquery"], 0, tensor_cores=True)
+    assert np.array_equal(ids, g["bf_ids"]) and np.array_equal(dists, g["bf_dists"])  # == the reference's own output
 
 
 # ------------------------------------------------------------------------------------------------
