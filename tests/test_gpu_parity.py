@@ -118,7 +118,7 @@ def test_bf_query_tensor_core_path_bit_exact_vs_oracle(N, Nq, D, K, kind):
 def test_bf_query_tensor_core_path_candidate_overflow_falls_back_exactly(golden):
     """all base rows (nearly) equidistant: every row is a candidate, the lists overflow, the exact scan takes over"""
     rng = np.random.default_rng(3)
-    base = np.tile(rng.random((1, 128), dtype=np.float32), (6000, 1))
+    base = np.tile(rng.random((1, 128), dtype=np.float32), (12000, 1))  # > the 8192-entry candidate capacity
     base[::7] += 1e-3
     query = rng.random((40, 128), dtype=np.float32)
     ids, dists = c_bf(base, query, 10, 0, tensor_cores=True)
