@@ -219,9 +219,11 @@ class GGNN:
 
     # ---- query ----
     def _counter(self, device):
-        if device not in self._work_counters:
-            self._work_counters[device] = torch.zeros(1, dtype=torch.int32, device=device)
-        return self._work_counters[device]
+        # one scheduling counter per (device, stream): batches enqueued on different streams may overlap
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        if key not in self._work_counters:
+            self._work_counters[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._work_counters[key]
 
     def _query_device(self, gpu_index, q_dev, k_query, tau_query, max_iterations, measure):
         """all shards of one GPU -> sorted [Nq, K] ids (GPU-local numbering) + dists on that GPU"""

@@ -389,3 +389,20 @@ def test_full_size_properties(big):
     sids, sd = idx.query(base[:1000].contiguous(), 1, 0.64, 400)
     assert float((sids[:, 0] == torch.arange(1000, device="cuda", dtype=torch.int32)).float().mean()) > 0.99
     assert float(sd.min()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# C++ host API (include/ggnn/ggnn.hpp)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("exe", ["ggnn_main", "ref_ggnn_main_on_b200"])
+def test_cpp_api_example_programs_run(exe):
+    """examples/ggnn_main: our example; ref_ggnn_main_on_b200: the REFERENCE's unmodified example program
+    (examples/cpp-and-cuda/ggnn_main.cpp) compiled against include/ggnn/base/ggnn.cuh of this repo"""
+    import os
+    import subprocess
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", exe)
+    if not os.path.exists(path):
+        pytest.skip(f"{exe} not built (needs __graft_entry__.build() in the container that has the sources)")
+    p = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "base[" in p.stdout.lower() or "recall" in p.stdout.lower()
