@@ -231,6 +231,8 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   a.off_bar = off;
   off += 16;
   a.warp_smem_bytes = align_up(off, 128);
+  // very long rows (D up to 4096 = 16 KB): fewer warps per CTA until the CTA fits
+  while (static_cast<size_t>(a.warp_smem_bytes) * a.warps_per_cta > dev.smem_per_block_optin && a.warps_per_cta > 1) a.warps_per_cta /= 2;
   const size_t smem = static_cast<size_t>(a.warp_smem_bytes) * a.warps_per_cta;
   if (smem > dev.smem_per_block_optin)
     return set_error(GGNN_B200_ERR_UNSUPPORTED, "per-CTA shared memory exceeds the device limit for this D");

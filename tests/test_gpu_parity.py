@@ -171,6 +171,30 @@ def test_query_bit_exact_vs_oracle_on_oracle_built_graph(K, tau, max_it, D, meas
     assert np.array_equal(st, o_st)  # pops / distance evaluations (roofline accounting)
 
 
+def test_query_edge_cases_vs_oracle():
+    """ragged / extreme shapes: one query, zero queries, k_build > 32 (two adjacency chunks per anchor), tiny base,
+    D = 4, long rows (D = 2048 -> one warp per CTA), graph rows containing -1 and duplicate ids"""
+    rng = np.random.default_rng(5).random(40000, dtype=np.float32) * 0.999 + 0.0005
+    for N, D, KB, K, Nq in ((3000, 64, 40, 10, 1), (400, 128, 24, 10, 33), (2000, 4, 24, 5, 50), (1200, 2048, 24, 10, 7)):
+        base, query = gen_data(N, max(Nq, 1), D, seed=N + D)
+        cfg = O.graph_config(N, D, KB)
+        gr = O.build_graph(cfg, base, 0.5, rng, 0)
+        g0 = gr.layer_graph(0).copy()
+        g0[5, 3] = -1              # unfilled slot (EMPTY_KEY), as `top` leaves them for tiny segments
+        g0[7, 4] = g0[7, 2]        # duplicate neighbour id inside one row
+        ids, dists = c_query(base, query[:Nq], g0, gr.start_points(), gr.nn1_stats, K, 0.8, 400, 0)
+        o_ids, o_d = O.query(base, query[:Nq], g0, gr.start_points(), gr.nn1_stats, K, 0.8, 400, 0)
+        assert np.array_equal(ids, o_ids) and np.array_equal(dists, o_d), (N, D, KB)
+    # zero queries: a no-op that succeeds
+    p = _lib.QueryParams()
+    assert _lib.lib().ggnn_b200_query(C.byref(p), 0, None) in (0, _lib.ERR_INVALID)
+    b = _lib.BfQueryParams()
+    t = torch.zeros(16, device="cuda")
+    b.D, b.measure, b.KQuery, b.N_base = 4, 0, 1, 4
+    b.d_base = b.d_query = b.d_query_results = t.data_ptr()
+    assert _lib.lib().ggnn_b200_bf_query(C.byref(b), 0, None) == 0
+
+
 def test_query_multi_shard_layout_and_merge():
     """[Nq, K*spg] interleaved layout + id offsets (query_layer.cu:81-90) and the device merge"""
     N, Nq, D, K = 2000, 64, 64, 10
