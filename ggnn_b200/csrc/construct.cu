@@ -55,7 +55,7 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   pl.stage_rows = env_u32("GGNN_B200_BUILD_STAGE_ROWS", rows);
   if (pl.stage_rows % 8 || pl.stage_rows == 0 || pl.stage_rows > 32) pl.stage_rows = rows;
   rows = pl.stage_rows;
-  pl.stage_mode = env_u32("GGNN_B200_STAGE_MODE", 0);
+  pl.stage_mode = (D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 0);  // rows must be 16-byte multiples to be staged
   uint32_t off = align_up(rows * row_bytes, 16);
   pl.off_sq = off;
   off += need_sq ? align_up(row_bytes, 16) : 0;
@@ -638,6 +638,20 @@ __device__ __forceinline__ void sym_stage_and_dist(WarpSmem& ws, const SymVec<FA
   const int lane = lane_id();
   const uint32_t D = sv.cfg.D;
   const int r = lane - b0;
+  if constexpr (!FAST) {
+    if (ws.stage_mode == 2) {  // unaligned rows: straight from global memory
+      for (int i = 0; i < nb; ++i) {
+        const int mi = __shfl_sync(FULL, m, b0 + i);
+        float dq, dh;
+        sym_dist_generic(sv.cfg, base + static_cast<size_t>(mi) * D, sv.s_q, sv.s_h, sv.q_norm, sv.h_norm, dq, dh);
+        if (r == i) {
+          mine_q = dq;
+          mine_h = dh;
+        }
+      }
+      return;
+    }
+  }
   stage_rows_g2s(ws, base, D, m, b0, nb);
   if constexpr (FAST) {
     for (int g = 0; g * 8 < nb; ++g) {
@@ -912,7 +926,6 @@ using namespace g200;
 static int check_cfg(const ggnn_b200_graph_config* cfg)
 {
   if (!cfg) return set_error(GGNN_B200_ERR_INVALID, "null graph config");
-  if (cfg->D % 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "D must be a multiple of 4 (16-byte rows for bulk copies)");
   if (cfg->KBuild > 111) return set_error(GGNN_B200_ERR_UNSUPPORTED, "KBuild > 111 not built yet");
   return 0;
 }

@@ -190,7 +190,6 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   if (N_query == 0) return 0;
   const int NS = p.sorted_size / 32;
   if (NS > 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "sorted_size > 128 (KQuery > 111) not built yet");
-  if (p.D % 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "D must be a multiple of 4 (16-byte rows for bulk copies)");
   if (p.d_work_counter) {
     cudaError_t e = cudaMemsetAsync(p.d_work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(work counter)");
@@ -217,7 +216,7 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   rows = env_u32("GGNN_B200_QUERY_STAGE_ROWS", rows);
   if (rows % 8 || rows == 0 || rows > 32) return set_error(GGNN_B200_ERR_INVALID, "stage rows must be 8, 16, 24 or 32");
   a.stage_rows = rows;
-  a.stage_mode = env_u32("GGNN_B200_STAGE_MODE", 0);
+  a.stage_mode = (p.D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 0);  // rows must be 16-byte multiples to be staged
   a.prefetch = env_u32("GGNN_B200_QUERY_PREFETCH", 1);
   uint32_t off = align_up(rows * row_bytes, 16);
   a.off_sq = off;

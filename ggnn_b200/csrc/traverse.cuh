@@ -16,7 +16,8 @@ struct WarpSmem {
   uint64_t* bar;     // mbarrier for the bulk copies
   uint32_t parity;   // phase of `bar`
   uint32_t stage_rows;  // multiple of 8
-  uint32_t stage_mode;  // 0: one cp.async.bulk (TMA engine) per row; 1: 16-byte cp.async per lane (LDGSTS)
+  uint32_t stage_mode;  // 0: one cp.async.bulk (TMA engine) per row; 1: 16-byte cp.async per lane (LDGSTS);
+                        // 2: no staging -- rows are not 16-byte aligned (D % 4 != 0), distances read global memory
 };
 
 // Move rows [b0, b0+nb) of the candidate list (lane b0+r holds the base row index m of local row r) into
@@ -189,6 +190,19 @@ __device__ __forceinline__ float stage_and_dist(WarpSmem& ws, const QueryVec<FAS
   const int lane = lane_id();
   const uint32_t D = qv.cfg.D;
   const int r = lane - b0;
+  if constexpr (!FAST) {
+    if (ws.stage_mode == 2) {
+      float mine_g = G200_INF;
+      for (int i = 0; i < nb; ++i) {
+        const int mi = __shfl_sync(FULL, m, b0 + i);
+        float a, b;
+        dist_partials_generic(qv.cfg, base + static_cast<size_t>(mi) * D, qv.s_q, a, b);
+        const float d = qv.cfg.measure == 0 ? a : cosine_finish(a, b, qv.q_norm);
+        if (r == i) mine_g = d;
+      }
+      return mine_g;
+    }
+  }
   stage_rows_g2s(ws, base, D, m, b0, nb);
 
   float mine = G200_INF;

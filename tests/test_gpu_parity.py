@@ -175,7 +175,8 @@ def test_query_edge_cases_vs_oracle():
     """ragged / extreme shapes: one query, zero queries, k_build > 32 (two adjacency chunks per anchor), tiny base,
     D = 4, long rows (D = 2048 -> one warp per CTA), graph rows containing -1 and duplicate ids"""
     rng = np.random.default_rng(5).random(40000, dtype=np.float32) * 0.999 + 0.0005
-    for N, D, KB, K, Nq in ((3000, 64, 40, 10, 1), (400, 128, 24, 10, 33), (2000, 4, 24, 5, 50), (1200, 2048, 24, 10, 7)):
+    for N, D, KB, K, Nq in ((3000, 64, 40, 10, 1), (400, 128, 24, 10, 33), (2000, 4, 24, 5, 50), (1200, 2048, 24, 10, 7),
+                            (1500, 30, 24, 10, 40), (900, 131, 24, 10, 20)):  # last two: rows not 16-byte multiples
         base, query = gen_data(N, max(Nq, 1), D, seed=N + D)
         cfg = O.graph_config(N, D, KB)
         gr = O.build_graph(cfg, base, 0.5, rng, 0)
@@ -236,7 +237,7 @@ class DevGraph:
 
 
 @pytest.mark.parametrize("D,measure,kind,N", [(128, 0, "uniform", 5000), (96, 1, "normal", 4000), (64, 0, "uniform", 1500),
-                                              (200, 0, "uniform", 1200)])
+                                              (200, 0, "uniform", 1200), (50, 0, "uniform", 1000), (33, 1, "normal", 900)])
 def test_construction_kernels_bit_exact_vs_oracle(D, measure, kind, N):
     K, tau = 24, 0.5
     base, _ = gen_data(N, 1, D, seed=D + N, kind=kind)
