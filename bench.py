@@ -49,6 +49,19 @@ def gen_gpu(N, Nq, D, kind, seed, device, shard_index=0):
     gb = torch.Generator(device=device).manual_seed(seed + 17 * (shard_index + 1))
     if kind == "uniform":
         return torch.rand((N, D), generator=gb, device=device), torch.rand((Nq, D), generator=g, device=device)
+    if kind.startswith("manifoldcos"):  # DEEP-like: unit-normalised vectors with low intrinsic dimension (cosine)
+        d = int(kind[len("manifoldcos"):] or 8)
+        A = torch.randn((d, D), generator=g, device=device) / (d ** 0.5)
+
+        def draw_c(n, gen):
+            out = torch.empty((n, D), device=device)
+            for lo in range(0, n, 1 << 20):
+                m = min(1 << 20, n - lo)
+                x = torch.randn((m, d), generator=gen, device=device) @ A + 0.02 * torch.randn((m, D), generator=gen, device=device)
+                out[lo:lo + m] = x / x.norm(dim=1, keepdim=True)
+            return out
+        query = draw_c(Nq, g)
+        return draw_c(N, gb), query
     if kind.startswith("manifold"):
         d = int(kind[len("manifold"):] or 16)
         A = torch.randn((d, D), generator=g, device=device) / (d ** 0.5)
