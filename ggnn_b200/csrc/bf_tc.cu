@@ -604,7 +604,7 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ra.cap = cap;
   ra.cand = w.cand;
   ra.cnt = w.cnt;
-  ra.warp_smem_bytes = align_up(32 * D * 4 + 16, 128);
+  ra.warp_smem_bytes = align_up(32 * D * 4 + 32, 128);
   const size_t rsmem = static_cast<size_t>(ra.warp_smem_bytes) * 4;
   auto rr = tc_rerank_kernel<KB>;
   if ((e = cudaFuncSetAttribute(rr, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem))) != cudaSuccess)

@@ -48,7 +48,7 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   pl.ring_cap = (vcap && vcap < max_pops) ? vcap : 0;
   pl.hsize = cache ? std::max(64u, 2u * bit_ceil_u32(std::max(1u, max_pops))) : 0;
   const uint32_t fixed = (need_sq ? align_up(row_bytes, 16) : 0) + (need_half ? align_up(row_bytes, 16) : 0) +
-                         align_up(sorted * 4, 16) + pl.hsize * 4 + align_up(pl.ring_cap * 4, 16) + 16;
+                         align_up(sorted * 4, 16) + pl.hsize * 4 + align_up(pl.ring_cap * 4, 16) + 32;
   const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / CW + 1)) / target_warps_per_sm;
   uint32_t rows = budget > fixed ? (budget - fixed) / row_bytes : 0;
   rows = std::max(8u, std::min(32u, rows / 8 * 8));
@@ -68,7 +68,7 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   pl.off_ring = off;
   off += align_up(pl.ring_cap * 4, 16);
   pl.off_bar = off;
-  off += 16;
+  off += 32;
   pl.warp_smem_bytes = align_up(off, 128);
   if (static_cast<size_t>(pl.warp_smem_bytes) * CW > dev.smem_per_block_optin)
     return set_error(GGNN_B200_ERR_UNSUPPORTED, "per-CTA shared memory exceeds the device limit for this D");
@@ -85,7 +85,7 @@ __device__ __forceinline__ void init_warp_smem(WarpSmem& ws, VisitedSet& V, unsi
   ws.parity = 0;
   ws.stage_rows = pl.stage_rows;
   ws.stage_mode = pl.stage_mode;
-  if (lane_id() == 0) mbar_init(ws.bar, 1);
+  if (lane_id() < 4) mbar_init(&ws.bar[lane_id()], 1);
   mbar_fence_init();
   __syncwarp();
   V.tab = reinterpret_cast<int*>(wbase + pl.off_hash);

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
   ws.parity = 0;
   ws.stage_rows = a.stage_rows;
   ws.stage_mode = a.stage_mode;
-  if (lane == 0) mbar_init(ws.bar, 1);
+  if (lane < 4) mbar_init(&ws.bar[lane], 1);
   mbar_fence_init();
   __syncwarp();
 
@@ -206,7 +206,7 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   a.ring_cap = (vcap < p.max_iterations) ? vcap : 0;
   a.hsize = std::max(64u, 2u * bit_ceil_u32(std::max(1u, p.max_iterations)));
   const uint32_t fixed = (fast ? 0 : align_up(row_bytes, 16)) + p.sorted_size * 4 + a.hsize * 4 +
-                         align_up(a.ring_cap * 4, 16) + 16;
+                         align_up(a.ring_cap * 4, 16) + 32;
   a.warps_per_cta = std::min(4u, std::max(1u, env_u32("GGNN_B200_QUERY_WARPS", 4)));
   const uint32_t target_warps_per_sm = env_u32("GGNN_B200_QUERY_WARPS_PER_SM", 24);
   const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / a.warps_per_cta + 1)) / target_warps_per_sm;
@@ -228,7 +228,7 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   a.off_ring = off;
   off += align_up(a.ring_cap * 4, 16);
   a.off_bar = off;
-  off += 16;
+  off += 32;
   a.warp_smem_bytes = align_up(off, 128);
   // very long rows (D up to 4096 = 16 KB): fewer warps per CTA until the CTA fits
   while (static_cast<size_t>(a.warp_smem_bytes) * a.warps_per_cta > dev.smem_per_block_optin && a.warps_per_cta > 1) a.warps_per_cta /= 2;

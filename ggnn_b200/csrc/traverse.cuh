@@ -13,8 +13,8 @@ struct WarpSmem {
   float* stage;      // [stage_rows * D], 16-byte aligned
   float* s_q;        // [D] query copy (generic distance path / sym half-way point), may be null
   int* s_sorted;     // [32*NS] mirror of the sorted keys for the filter
-  uint64_t* bar;     // mbarrier for the bulk copies
-  uint32_t parity;   // phase of `bar`
+  uint64_t* bar;     // mbarriers for the bulk copies: bar[0..3], one per 8-row stage group
+  uint32_t parity;   // phase bit of bar[i] in bit i
   uint32_t stage_rows;  // multiple of 8
   uint32_t stage_mode;  // 0: one cp.async.bulk (TMA engine) per row; 1: 16-byte cp.async per lane (LDGSTS);
                         // 2: no staging -- rows are not 16-byte aligned (D % 4 != 0), distances read global memory
@@ -31,8 +31,8 @@ __device__ __forceinline__ void stage_rows_g2s(WarpSmem& ws, const float* __rest
     __syncwarp();
     const int r = lane - b0;
     if (r >= 0 && r < nb) bulk_g2s(ws.stage + static_cast<size_t>(r) * D, base + static_cast<size_t>(m) * D, row_bytes, ws.bar);
-    mbar_wait(ws.bar, ws.parity);
-    ws.parity ^= 1;
+    mbar_wait(ws.bar, ws.parity & 1u);
+    ws.parity ^= 1u;
   }
   else {
     const uint32_t chunks = row_bytes >> 4;
@@ -259,10 +259,40 @@ __device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, War
   if (lane < cnt) m = translation ? translation[key_r] : key_r;
 
   float mine = G200_INF;
-  for (int b0 = 0; b0 < cnt; b0 += ws.stage_rows) {
-    const int nb = min(static_cast<int>(ws.stage_rows), cnt - b0);
-    const float d = stage_and_dist<FAST, D32, NW>(ws, qv, base, m, b0, nb);
-    if (lane >= b0 && lane < b0 + nb) mine = d;
+  if (FAST && ws.stage_mode == 0 && ws.stage_rows >= 16) {
+    // software pipeline over 8-row groups: group g lives in buffer g % NBUF with its own mbarrier, so the copies
+    // of the next groups are in flight while the distances of the current one are computed
+    constexpr int D = 32 * D32;
+    const int nbuf = static_cast<int>(ws.stage_rows >> 3);
+    const int ngroups = (cnt + 7) >> 3;
+    auto issue = [&](int g) {
+      const int buf = g % nbuf;
+      const int nr = min(8, cnt - 8 * g);
+      if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>(nr) * D * 4u);
+      __syncwarp();
+      const int r = lane - 8 * g;
+      if (r >= 0 && r < nr)
+        bulk_g2s(ws.stage + static_cast<size_t>(buf * 8 + r) * D, base + static_cast<size_t>(m) * D, D * 4u, &ws.bar[buf]);
+    };
+    for (int g = 0; g < min(nbuf, ngroups); ++g) issue(g);
+    for (int g = 0; g < ngroups; ++g) {
+      const int buf = g % nbuf;
+      mbar_wait(&ws.bar[buf], (ws.parity >> buf) & 1u);
+      ws.parity ^= 1u << buf;
+      if constexpr (FAST) {
+        const float dg = dist8_fast<D32, NW>(ws.stage + static_cast<size_t>(buf) * 8 * D, min(8, cnt - 8 * g), qv.cfg.measure, qv.q, qv.q_norm);
+        if ((lane >> 3) == g) mine = dg;
+      }
+      __syncwarp();  // the group's rows have been read: its buffer may be refilled
+      if (g + nbuf < ngroups) issue(g + nbuf);
+    }
+  }
+  else {
+    for (int b0 = 0; b0 < cnt; b0 += ws.stage_rows) {
+      const int nb = min(static_cast<int>(ws.stage_rows), cnt - b0);
+      const float d = stage_and_dist<FAST, D32, NW>(ws, qv, base, m, b0, nb);
+      if (lane >= b0 && lane < b0 + nb) mine = d;
+    }
   }
 
   if (pf_graph) {
