@@ -1057,7 +1057,7 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
   FastSel f = fast_sel(a.D, a.VB, a.items);
   const int NS = a.sorted / 32;
   f.fast = f.fast && f.nw == 1 && NS == 2;  // the register-resident variants that are instantiated
-  if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, 24)) return rc;
+  if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, 16)) return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
   int rc = -1;
 #define G200_MERGE(NS_, FAST_, D32_, NW_) \
@@ -1122,7 +1122,7 @@ extern "C" int ggnn_b200_sym(const ggnn_b200_graph_config* cfg, const float* d_b
   FastSel f = fast_sel(a.D, a.VB, a.items);
   const int NS = a.sorted / 32;
   f.fast = f.fast && f.nw == 2 && NS == 2;
-  if (int rc = make_plan(a.pl, a.D, !f.fast, !f.fast, a.sorted, a.cache, a.max_iterations, 24)) return rc;
+  if (int rc = make_plan(a.pl, a.D, !f.fast, !f.fast, a.sorted, a.cache, a.max_iterations, 16)) return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
 #define G200_SYM(NS_, FAST_, D32_, NW_) \
   return launch_warp_kernel(sym_kernel<NS_, FAST_, D32_, NW_>, a, a.N_layer, smem, stream, "sym_kernel")

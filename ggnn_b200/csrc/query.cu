@@ -208,7 +208,7 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   const uint32_t fixed = (fast ? 0 : align_up(row_bytes, 16)) + p.sorted_size * 4 + a.hsize * 4 +
                          align_up(a.ring_cap * 4, 16) + 32;
   a.warps_per_cta = std::min(4u, std::max(1u, env_u32("GGNN_B200_QUERY_WARPS", 4)));
-  const uint32_t target_warps_per_sm = env_u32("GGNN_B200_QUERY_WARPS_PER_SM", 24);
+  const uint32_t target_warps_per_sm = env_u32("GGNN_B200_QUERY_WARPS_PER_SM", 16);
   const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / a.warps_per_cta + 1)) / target_warps_per_sm;
   uint32_t rows = budget > fixed ? (budget - fixed) / row_bytes : 0;
   rows = std::min(32u, rows / 8 * 8);
