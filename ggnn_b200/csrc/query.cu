@@ -21,7 +21,7 @@ struct QueryArgs {
   uint32_t warp_smem_bytes;
   uint32_t stage_rows;
   uint32_t stage_mode;
-  uint32_t prefetch;   // 1: L2-prefetch the adjacency rows of promising candidates
+  uint32_t prefetch;   // 0 off; 1: L2-prefetch the adjacency rows of promising candidates; 2: speculative next-anchor load
   uint32_t hsize;      // visited hash slots (power of two)
   uint32_t ring_cap;   // 0 = ring mirror not needed
   uint32_t off_sq, off_sorted, off_hash, off_ring, off_bar;  // byte offsets in the per-warp block
@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
                                     p.KBuild);
     }
 
+    SpecRow spec{EMPTY_KEY, EMPTY_KEY};
+    const bool use_spec = a.prefetch >= 2 && p.KBuild <= 32;
     for (uint32_t ite = 0; ite < p.max_iterations; ++ite) {
       // :58-63
       const float best0 = L.dist_at(0);
@@ -96,11 +98,14 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
       st.pops++;
       // :69-76
       for (uint32_t i = 0; i < p.KBuild; i += 32) {
-        const int ck = (i + lane < p.KBuild)
-                           ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane)
-                           : EMPTY_KEY;
+        int ck;
+        if (use_spec && spec.key == anchor)
+          ck = spec.row;  // the speculative load issued before the previous push loop was right
+        else
+          ck = (i + lane < p.KBuild) ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane) : EMPTY_KEY;
+        spec.key = EMPTY_KEY;
         fetch<NS, FAST, NI, 1, true>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
-                                     p.KBuild);
+                                     p.KBuild, use_spec ? &spec : nullptr);
       }
     }
 
@@ -217,7 +222,7 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   if (rows % 8 || rows == 0 || rows > 32) return set_error(GGNN_B200_ERR_INVALID, "stage rows must be 8, 16, 24 or 32");
   a.stage_rows = rows;
   a.stage_mode = (p.D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 0);  // rows must be 16-byte multiples to be staged
-  a.prefetch = env_u32("GGNN_B200_QUERY_PREFETCH", 1);
+  a.prefetch = env_u32("GGNN_B200_QUERY_PREFETCH", 2);  // 0 off, 1 L2 prefetch of candidate rows, 2 speculative next-anchor row load
   uint32_t off = align_up(rows * row_bytes, 16);
   a.off_sq = off;
   off += fast ? 0 : align_up(row_bytes, 16);

@@ -230,11 +230,20 @@ __device__ __forceinline__ float stage_and_dist(WarpSmem& ws, const QueryVec<FAS
 //   pf_graph/pf_stride: if non-null, the adjacency row of every candidate that passes the criteria at
 //             first sight (a likely future anchor) is prefetched into L2 -- the pop -> adjacency load is the
 //             serial latency chain of the traversal and DRAM bandwidth is plentiful
+// Speculative load of the next anchor's adjacency row (SpecRow): before the (serial, ~2k-cycle) push loop the next
+// pop is already predictable -- it is the better of the current prioQ head and the best new candidate -- so its
+// adjacency row is requested then and arrives while the pushes run; the caller checks the prediction after pop().
+struct SpecRow {
+  int key;  // predicted anchor (EMPTY_KEY = none), uniform
+  int row;  // lane l: adjacency entry l of `key`
+};
+
 template <int NS, bool FAST, int D32, int NW, bool FILTER>
 __device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, WarpSmem& ws,
                                       const QueryVec<FAST, D32, NW>& qv, const float* __restrict__ base,
                                       const int* __restrict__ translation, int ck, float xi, Stats& st,
-                                      const int* __restrict__ pf_graph = nullptr, uint32_t pf_stride = 0)
+                                      const int* __restrict__ pf_graph = nullptr, uint32_t pf_stride = 0,
+                                      SpecRow* spec = nullptr)
 {
   const int lane = lane_id();
   bool valid = ck != EMPTY_KEY;
@@ -297,7 +306,24 @@ __device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, War
 
   if (pf_graph) {
     const float crit0 = L.dist_at(L.BEST - 1) + xi;
-    if (lane < cnt && mine < crit0) {
+    const bool pass = lane < cnt && mine < crit0;
+    if (spec && pf_stride <= 32) {
+      // predicted next anchor = min(current prioQ head, best passing candidate); distances are >= 0, so their bit
+      // patterns order like unsigned integers
+      const unsigned mbits = pass ? __float_as_uint(mine) : 0x7f800000u;
+      const unsigned best_bits = __reduce_min_sync(FULL, mbits);
+      const float head_d = L.dist_at(L.head);
+      int pred = L.key_at(L.head);
+      if (__uint_as_float(best_bits) < head_d) {
+        const unsigned who = __ballot_sync(FULL, pass && mbits == best_bits);
+        pred = __shfl_sync(FULL, key_r, __ffs(who) - 1);
+      }
+      spec->key = pred;
+      if (pred != EMPTY_KEY)
+        spec->row = (static_cast<uint32_t>(lane) < pf_stride) ? __ldg(pf_graph + static_cast<size_t>(pred) * pf_stride + lane)
+                                                            : EMPTY_KEY;
+    }
+    else if (pass) {
       const int* row = pf_graph + static_cast<size_t>(key_r) * pf_stride;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(row + pf_stride - 1));

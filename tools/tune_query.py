@@ -27,7 +27,7 @@ def main():
         idx.set_base(base)
         idx.build(24, 0.5, 2)
         ref_ids = None
-        for pf, mode, rows in itertools.product((0, 1), modes, rows_l):
+        for pf, mode, rows in itertools.product((1, 2), modes, rows_l):
             os.environ["GGNN_B200_QUERY_PREFETCH"] = str(pf)
             os.environ["GGNN_B200_STAGE_MODE"] = str(mode)
             os.environ["GGNN_B200_QUERY_STAGE_ROWS"] = str(rows)
