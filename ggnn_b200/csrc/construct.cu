@@ -449,15 +449,21 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
       const int ck = lane == 0 ? static_cast<int>(n) : EMPTY_KEY;
       fetch<NS, FAST, D32, NW, false>(L, V, ws, qv, a.base, tr, ck, xi, st);
     }
+    const int32_t* layer_graph = a.graph + static_cast<size_t>(a.Ns_offsets[layer]) * K;
+    SpecRow spec{EMPTY_KEY, EMPTY_KEY};
+    const bool use_spec = K <= 32;
     for (uint32_t ite = 0; ite < a.max_iterations; ++ite) {
       const float crit = L.dist_at(L.BEST - 1) + xi;
       const int anchor = L.pop(crit);
       if (anchor == EMPTY_KEY) break;
       V.insert(anchor);
       for (uint32_t j = 0; j < K; j += 32) {
-        const int ck = (j + lane < K) ? __ldg(a.graph + (static_cast<size_t>(a.Ns_offsets[layer]) + anchor) * K + j + lane)
-                                      : EMPTY_KEY;
-        fetch<NS, FAST, D32, NW, true>(L, V, ws, qv, a.base, tr, ck, xi, st);
+        int ck;
+        if (use_spec && spec.key == anchor) ck = spec.row;  // speculative load issued before the previous push loop
+        else ck = (j + lane < K) ? __ldg(layer_graph + static_cast<size_t>(anchor) * K + j + lane) : EMPTY_KEY;
+        spec.key = EMPTY_KEY;
+        fetch<NS, FAST, D32, NW, true>(L, V, ws, qv, a.base, tr, ck, xi, st, use_spec ? layer_graph : nullptr, K,
+                                       use_spec ? &spec : nullptr);
       }
     }
   }
