@@ -108,6 +108,7 @@ class GGNN:
         self._kbuild = None
         self._measure = None
         self._work_counters = {}
+        self._base_dtype = torch.float32
 
     # ---- configuration (ggnn.cu:53-60, 420-454) ----
     def set_working_directory(self, path):
@@ -136,13 +137,18 @@ class GGNN:
 
     def set_base(self, base):
         base = _as_tensor(base, "base")
-        if base.dtype != torch.float32:
-            raise NotImplementedError("only float32 base vectors are built (uint8 is a 'next' row)")
+        if base.dtype not in (torch.float32, torch.uint8):
+            raise TypeError("base must be float32 or uint8 (lib.h:26-28)")
+        # uint8 base vectors (the reference's BaseT = uint8_t instantiation, lib.h:26-28): every distance of the
+        # reference is computed on static_cast<float>(value) (distance.cuh:131-148), so widening the vectors to
+        # fp32 once gives bit-identical results with the fp32 kernels.  (A native 1-byte row format -- 4x less gather
+        # traffic -- is the next step)
+        self._base_dtype = base.dtype
         if self._shards:
             raise RuntimeError("base cannot be changed after the graph has been set up")
         if not (self.MIN_D <= base.shape[1] <= self.MAX_D):
             raise ValueError("unsupported dimension")
-        self._base = base.contiguous()  # the reference copies its input as well (nanobind.cu:102-110)
+        self._base = base.contiguous().float() if base.dtype == torch.uint8 else base.contiguous()  # (the reference copies too)
 
     # ---- sharding (ggnn.cu:154-203) ----
     def _prepare(self, k_build):
@@ -260,8 +266,10 @@ class GGNN:
         if not self._shards or self._shards[0].graph is None:
             raise RuntimeError("There is no graph to query.")
         query = _as_tensor(query, "query")
-        if query.dtype != self._base.dtype:
+        if query.dtype != getattr(self, "_base_dtype", torch.float32):
             raise ValueError("query data type has to match base data type")  # ggnn.cu:524-540
+        if query.dtype == torch.uint8:
+            query = query.float()
         if query.shape[1] != self._base.shape[1]:
             raise ValueError("query dimension does not match the base")
         l = _lib.lib()
@@ -303,6 +311,10 @@ class GGNN:
         if not torch.cuda.is_available():
             raise RuntimeError("ggnn_b200 needs a CUDA device (there is no CPU fallback)")
         query = _as_tensor(query, "query")
+        if query.dtype != getattr(self, "_base_dtype", torch.float32):
+            raise ValueError("query data type has to match base data type")
+        if query.dtype == torch.uint8:
+            query = query.float()
         dev = torch.device("cuda", self._gpus[0])
         l = _lib.lib()
         with torch.cuda.device(dev):

@@ -431,3 +431,26 @@ def test_cpp_api_example_programs_run(exe):
     p = subprocess.run([path], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "base[" in p.stdout.lower() or "recall" in p.stdout.lower()
+
+
+def test_uint8_base_vectors_match_oracle_on_widened_values():
+    """BaseT = uint8_t (lib.h:26-28): the reference computes on static_cast<float>(value), so results must equal the
+    fp32 path / oracle on the widened vectors; query dtype must match the base dtype (ggnn.cu:524-540)"""
+    rng = np.random.default_rng(2)
+    base_u8 = rng.integers(0, 256, (6000, 128), dtype=np.uint8)
+    query_u8 = rng.integers(0, 256, (300, 128), dtype=np.uint8)
+    g = ggnn.GGNN()
+    g.set_base(torch.from_numpy(base_u8))
+    g.build(24, 0.5)
+    with pytest.raises(ValueError):
+        g.query(torch.from_numpy(query_u8).float(), 10, 0.64)
+    ids, dists = g.query(torch.from_numpy(query_u8), 10, 0.64, 400)
+    gt, gtd = g.bf_query(torch.from_numpy(query_u8), 10)
+    bf, qf = base_u8.astype(np.float32), query_u8.astype(np.float32)
+    o_gt, o_gtd = O.bf_query(bf, qf[:64], 10)
+    assert np.array_equal(gt.numpy()[:64], o_gt) and np.array_equal(gtd.numpy()[:64], o_gtd)
+    gr = g.get_graph(0)
+    o_ids, o_d = O.query(bf, qf, gr.layer_graph(0).cpu().numpy(), gr.layer_translation(3).cpu().numpy(),
+                         gr.nn1_stats.cpu().numpy(), 10, 0.64, 400)
+    assert np.array_equal(ids.numpy(), o_ids) and np.array_equal(dists.numpy(), o_d)
+    assert float(dists.numpy()[0, 0]) == float(int(dists.numpy()[0, 0]))  # integer-valued squared distances

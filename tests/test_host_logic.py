@@ -33,8 +33,9 @@ def test_misuse_raises_like_the_reference():
         g.store()
     with pytest.raises(ValueError):
         g.set_base(torch.zeros(10, 5000))     # D > 4096
-    with pytest.raises(NotImplementedError):
-        g.set_base(torch.zeros(10, 8, dtype=torch.uint8))
+    with pytest.raises(TypeError):
+        g.set_base(torch.zeros(10, 8, dtype=torch.int32))
+    g.set_base(torch.zeros(10, 8, dtype=torch.uint8))   # uint8 base vectors are accepted (widened to fp32)
     g.set_base(torch.zeros(100, 8))
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
