@@ -66,6 +66,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
       ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (128 lanes = rows, one 32-bit column per tf32 K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_c), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
+{
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -122,12 +143,19 @@ struct TcGemmArgs {
   uint32_t rows_per_split;  // multiple of TC_BN
   const float* bnorm;       // [N_base]
   const float* qnorm;       // [N_query]
+  const float* q_hi;        // [N_query, D] split (-2*query), for the A-in-TMEM variant
+  const float* q_lo;
+  uint32_t D;
   const unsigned int* max_norm_bits;
   int32_t* cand;            // [N_query, cap]
   uint32_t* cnt;            // [N_query]
 };
 
-template <int KB>  // k-blocks: D = 32*KB
+// A_TMEM: the 128-row query tile (hi and lo) lives in tensor memory (columns 256..), so all shared memory goes
+// to the B ring (TC_STAGES_TMEM stages instead of TC_STAGES); otherwise A is in shared memory (TMA)
+constexpr int TC_STAGES_TMEM = 6;
+
+template <int KB, bool A_TMEM>  // k-blocks: D = 32*KB
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                    const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const TcGemmArgs a)
@@ -135,15 +163,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   extern __shared__ unsigned char smem_unaligned[];
   // carve-up (every operand tile 1024-byte aligned: required by the 128-byte swizzle)
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  unsigned char* sA_hi = smem;                                  // [KB][16 KB]
-  unsigned char* sA_lo = sA_hi + KB * TC_KBLOCK_BYTES;          // [KB][16 KB]
-  unsigned char* sB = sA_lo + KB * TC_KBLOCK_BYTES;             // [STAGES][hi 16 KB | lo 16 KB]
-  float* s_kbest = reinterpret_cast<float*>(sB + TC_STAGES * 2 * TC_KBLOCK_BYTES);  // [128][TC_KP]
+  constexpr int NSTAGE = A_TMEM ? TC_STAGES_TMEM : TC_STAGES;
+  constexpr int A_SMEM_KB = A_TMEM ? 0 : KB;
+  unsigned char* sA_hi = smem;                                  // [KB][16 KB] (not A_TMEM)
+  unsigned char* sA_lo = sA_hi + A_SMEM_KB * TC_KBLOCK_BYTES;   // [KB][16 KB]
+  unsigned char* sB = sA_lo + A_SMEM_KB * TC_KBLOCK_BYTES;      // [NSTAGE][hi 16 KB | lo 16 KB]
+  float* s_kbest = reinterpret_cast<float*>(sB + NSTAGE * 2 * TC_KBLOCK_BYTES);  // [128][TC_KP]
   float* s_bnorm = s_kbest + TC_BM * TC_KP;                     // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bnorm + 2 * TC_BN);
-  uint64_t* full = bars;                    // [STAGES]
-  uint64_t* empty = bars + TC_STAGES;       // [STAGES]
-  uint64_t* a_full = bars + 2 * TC_STAGES;  // [1]
+  uint64_t* full = bars;                    // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;          // [NSTAGE]
+  uint64_t* a_full = bars + 2 * NSTAGE;     // [1]
   uint64_t* t_full = a_full + 1;            // [2]
   uint64_t* t_empty = t_full + 2;           // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
@@ -156,19 +186,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t n_tiles = (n_end > n_begin) ? (n_end - n_begin + TC_BN - 1) / TC_BN : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(a_full, 1);
+    mbar_init(a_full, A_TMEM ? 4 : 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
       mbar_init(&t_empty[i], 4);
     }
     mbar_fence_init();
   }
-  if (warp == 2) {  // TMEM: 2 accumulators x 128 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256u) : "memory");
+  constexpr uint32_t TMEM_COLS = A_TMEM ? 512u : 256u;  // 2 accumulators x 128 columns (+ A hi/lo: 2 x 32*KB columns)
+  constexpr uint32_t COL_A_HI = 256u, COL_A_LO = 256u + 32u * KB;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -179,10 +211,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(a_full, 2 * KB * TC_KBLOCK_BYTES);
-      for (int kb = 0; kb < KB; ++kb) {
-        tma_load_2d(sA_hi + kb * TC_KBLOCK_BYTES, &tm_qhi, a_full, kb * TC_BK, static_cast<int>(q0));
-        tma_load_2d(sA_lo + kb * TC_KBLOCK_BYTES, &tm_qlo, a_full, kb * TC_BK, static_cast<int>(q0));
+      if constexpr (!A_TMEM) {
+        mbar_expect_tx(a_full, 2 * KB * TC_KBLOCK_BYTES);
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(sA_hi + kb * TC_KBLOCK_BYTES, &tm_qhi, a_full, kb * TC_BK, static_cast<int>(q0));
+          tma_load_2d(sA_lo + kb * TC_KBLOCK_BYTES, &tm_qlo, a_full, kb * TC_BK, static_cast<int>(q0));
+        }
       }
       uint32_t stage = 0, phase = 0;
       for (uint32_t t = 0; t < n_tiles; ++t) {
@@ -193,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           unsigned char* dst = sB + stage * 2 * TC_KBLOCK_BYTES;
           tma_load_2d(dst, &tm_bhi, &full[stage], kb * TC_BK, row);
           tma_load_2d(dst + TC_KBLOCK_BYTES, &tm_blo, &full[stage], kb * TC_BK, row);
-          if (++stage == TC_STAGES) {
+          if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
@@ -217,19 +251,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t da_hi = umma_desc_sw128(sA_hi + kb * TC_KBLOCK_BYTES);
-          const uint64_t da_lo = umma_desc_sw128(sA_lo + kb * TC_KBLOCK_BYTES);
           const uint64_t db_hi = umma_desc_sw128(sB + stage * 2 * TC_KBLOCK_BYTES);
           const uint64_t db_lo = umma_desc_sw128(sB + stage * 2 * TC_KBLOCK_BYTES + TC_KBLOCK_BYTES);
+          if constexpr (A_TMEM) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = +2 in the descriptor's 16-byte units
-            const uint64_t ko = static_cast<uint64_t>(2 * k);
-            umma_tf32(tmem_c, da_hi + ko, db_hi + ko, idesc, (kb | k) != 0);
-            umma_tf32(tmem_c, da_hi + ko, db_lo + ko, idesc, 1);
-            umma_tf32(tmem_c, da_lo + ko, db_hi + ko, idesc, 1);
+            for (int k = 0; k < TC_BK / 8; ++k) {  // A: +8 columns per UMMA_K; B: +2 descriptor units (32 bytes)
+              const uint64_t ko = static_cast<uint64_t>(2 * k);
+              const uint32_t a_hi = tmem_base + COL_A_HI + kb * TC_BK + k * 8;
+              const uint32_t a_lo = tmem_base + COL_A_LO + kb * TC_BK + k * 8;
+              umma_tf32_ts(tmem_c, a_hi, db_hi + ko, idesc, (kb | k) != 0);
+              umma_tf32_ts(tmem_c, a_hi, db_lo + ko, idesc, 1);
+              umma_tf32_ts(tmem_c, a_lo, db_hi + ko, idesc, 1);
+            }
+          }
+          else {
+            const uint64_t da_hi = umma_desc_sw128(sA_hi + kb * TC_KBLOCK_BYTES);
+            const uint64_t da_lo = umma_desc_sw128(sA_lo + kb * TC_KBLOCK_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = +2 in the descriptor's 16-byte units
+              const uint64_t ko = static_cast<uint64_t>(2 * k);
+              umma_tf32(tmem_c, da_hi + ko, db_hi + ko, idesc, (kb | k) != 0);
+              umma_tf32(tmem_c, da_hi + ko, db_lo + ko, idesc, 1);
+              umma_tf32(tmem_c, da_lo + ko, db_hi + ko, idesc, 1);
+            }
           }
           umma_commit(&empty[stage]);  // frees this B stage once the MMAs above have read it
-          if (++stage == TC_STAGES) {
+          if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
@@ -247,6 +294,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t K = a.K;
     float* kb = s_kbest + r * TC_KP;
     for (uint32_t i = 0; i < TC_KP; ++i) kb[i] = G200_INF;
+    if constexpr (A_TMEM) {
+      // this thread's query row (hi, lo halves of -2q) -> tensor memory lane r, one column per K element
+      for (int half = 0; half < 2; ++half) {
+        const float* src = (half ? a.q_lo : a.q_hi) + static_cast<size_t>(min(q, a.N_query - 1)) * a.D;
+        for (int c = 0; c < KB; ++c) {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 f = live ? reinterpret_cast<const float4*>(src + c * 32)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * j + 0] = __float_as_uint(f.x);
+            v[4 * j + 1] = __float_as_uint(f.y);
+            v[4 * j + 2] = __float_as_uint(f.z);
+            v[4 * j + 3] = __float_as_uint(f.w);
+          }
+          tmem_st32(tmem_base + (half ? COL_A_LO : COL_A_HI) + c * 32 + ((ew * 32u) << 16), v);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
     // error bound of the approximate score: 2^-13 * (|q|^2 + max |b|^2)
     const float margin = live ? ldexpf(a.qnorm[q] + __uint_as_float(*a.max_norm_bits), -13) : 0.f;
     float tau = G200_INF;  // K-th best approximate score so far (+inf until K rows were seen)
@@ -298,7 +367,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -591,8 +660,14 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ga.max_norm_bits = w.max_norm;
   ga.cand = w.cand;
   ga.cnt = w.cnt;
-  const size_t smem = 2 * KB * TC_KBLOCK_BYTES + TC_STAGES * 2 * TC_KBLOCK_BYTES + TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
-  auto gemm = tc_gemm_kernel<KB>;
+  ga.q_hi = w.q_hi;
+  ga.q_lo = w.q_lo;
+  ga.D = D;
+  const bool a_tmem = env_u32("GGNN_B200_BF_A_TMEM", 1) != 0;
+  const size_t smem_tail = TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
+  const size_t smem = (a_tmem ? static_cast<size_t>(TC_STAGES_TMEM) * 2 * TC_KBLOCK_BYTES
+                              : 2 * KB * TC_KBLOCK_BYTES + static_cast<size_t>(TC_STAGES) * 2 * TC_KBLOCK_BYTES) + smem_tail;
+  auto gemm = a_tmem ? tc_gemm_kernel<KB, true> : tc_gemm_kernel<KB, false>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
   gemm<<<dim3(q_tiles, splits), TC_THREADS, smem, stream>>>(tq_hi, tq_lo, tb_hi, tb_lo, ga);
