@@ -20,8 +20,6 @@
 #include "host_util.h"
 #include "../../include/ggnn_b200.h"
 
-#include <cuda.h>
-
 #include <algorithm>
 
 namespace g200 {
@@ -38,14 +36,6 @@ constexpr uint32_t TC_KBLOCK_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1)
-{
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
 }
 __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr)
 {
@@ -113,22 +103,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 
 // ---- stage 1: split + norms ---------------------------------------------------------------------
 // one warp per row; out rows padded with zeros up to n_rows_pad (TMA never reads past them anyway)
-__global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ x, uint32_t n_rows, uint32_t D, float scale,
-                                                       float* __restrict__ hi, float* __restrict__ lo,
-                                                       float* __restrict__ norms, unsigned int* __restrict__ max_norm_bits)
+// tiled != 0 (base operand): output is tile-major and PRE-SWIZZLED -- for every 128-row tile t and 32-column k-block
+// kb one contiguous 32 KB record [hi 16 KB | lo 16 KB] whose bytes are exactly the SWIZZLE_128B shared-memory image the
+// UMMA descriptor expects (16-byte chunk c of row r stored at chunk c ^ (r & 7)), so the GEMM streams B with ONE
+// linear 32 KB bulk copy per stage instead of 2 x 128 strided 128-byte row segments.  Rows past n_rows are zero.
+__global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ x, uint32_t n_rows, uint32_t n_rows_out,
+                                                       uint32_t D, float scale, int tiled, float* __restrict__ hi,
+                                                       float* __restrict__ lo, float* __restrict__ norms,
+                                                       unsigned int* __restrict__ max_norm_bits)
 {
   const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
+  if (row >= n_rows_out) return;
   const int lane = lane_id();
   float acc = 0.f;
+  const uint32_t KB = D / 32;
   for (uint32_t d = lane; d < D; d += 32) {
-    const float v = x[static_cast<size_t>(row) * D + d];
+    const float v = row < n_rows ? x[static_cast<size_t>(row) * D + d] : 0.f;
     acc = fmaf(v, v, acc);
     const float s = v * scale;  // scale is a power of two: exact
     const float h = __uint_as_float(__float_as_uint(s) & 0xffffe000u);
-    hi[static_cast<size_t>(row) * D + d] = h;
-    lo[static_cast<size_t>(row) * D + d] = s - h;  // exact
+    if (tiled) {
+      const uint32_t t = row >> 7, r = row & 127, kb = d >> 5, j = d & 31;
+      const size_t rec = (static_cast<size_t>(t) * KB + kb) * (2 * 4096);  // floats per 32 KB record
+      const uint32_t off = r * 32 + (((j >> 2) ^ (r & 7)) << 2) + (j & 3);
+      hi[rec + off] = h;           // `hi` is the record array; lo half follows at +4096 floats
+      hi[rec + 4096 + off] = s - h;
+    }
+    else {
+      hi[static_cast<size_t>(row) * D + d] = h;
+      lo[static_cast<size_t>(row) * D + d] = s - h;  // exact
+    }
   }
+  if (row >= n_rows) return;
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
   if (lane == 0) {
@@ -143,33 +149,29 @@ struct TcGemmArgs {
   uint32_t rows_per_split;  // multiple of TC_BN
   const float* bnorm;       // [N_base]
   const float* qnorm;       // [N_query]
-  const float* q_hi;        // [N_query, D] split (-2*query), for the A-in-TMEM variant
+  const float* q_hi;        // [N_query, D] hi / lo halves of -2*query (row-major)
   const float* q_lo;
+  const float* b_tiled;     // base operand, tile-major pre-swizzled records (see tc_split_kernel)
   uint32_t D;
   const unsigned int* max_norm_bits;
   int32_t* cand;            // [N_query, cap]
   uint32_t* cnt;            // [N_query]
 };
 
-// A_TMEM: the 128-row query tile (hi and lo) lives in tensor memory (columns 256..), so all shared memory goes
-// to the B ring (TC_STAGES_TMEM stages instead of TC_STAGES); otherwise A is in shared memory (TMA)
+// The 128-row query tile (hi and lo halves of -2q) lives in TENSOR MEMORY (columns 256..), written once per CTA with
+// tcgen05.st; all shared memory goes to the B ring.
 constexpr int TC_STAGES_TMEM = 6;
 
-template <int KB, bool A_TMEM>  // k-blocks: D = 32*KB
-__global__ void __launch_bounds__(TC_THREADS, 1)
-    tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
-                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, const TcGemmArgs a)
+template <int KB>  // k-blocks: D = 32*KB
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs a)
 {
   extern __shared__ unsigned char smem_unaligned[];
   // carve-up (every operand tile 1024-byte aligned: required by the 128-byte swizzle)
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  constexpr int NSTAGE = A_TMEM ? TC_STAGES_TMEM : TC_STAGES;
-  constexpr int A_SMEM_KB = A_TMEM ? 0 : KB;
-  unsigned char* sA_hi = smem;                                  // [KB][16 KB] (not A_TMEM)
-  unsigned char* sA_lo = sA_hi + A_SMEM_KB * TC_KBLOCK_BYTES;   // [KB][16 KB]
-  unsigned char* sB = sA_lo + A_SMEM_KB * TC_KBLOCK_BYTES;      // [NSTAGE][hi 16 KB | lo 16 KB]
-  float* s_kbest = reinterpret_cast<float*>(sB + NSTAGE * 2 * TC_KBLOCK_BYTES);  // [128][TC_KP]
-  float* s_bnorm = s_kbest + TC_BM * TC_KP;                     // [2][128]
+  constexpr int NSTAGE = TC_STAGES_TMEM;
+  unsigned char* sB = smem;                                                       // [NSTAGE][hi 16 KB | lo 16 KB]
+  float* s_kbest = reinterpret_cast<float*>(sB + NSTAGE * 2 * TC_KBLOCK_BYTES);   // [128][TC_KP]
+  float* s_bnorm = s_kbest + TC_BM * TC_KP;                                       // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bnorm + 2 * TC_BN);
   uint64_t* full = bars;                    // [NSTAGE]
   uint64_t* empty = bars + NSTAGE;          // [NSTAGE]
@@ -190,14 +192,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(a_full, A_TMEM ? 4 : 1);
+    mbar_init(a_full, 4);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
       mbar_init(&t_empty[i], 4);
     }
     mbar_fence_init();
   }
-  constexpr uint32_t TMEM_COLS = A_TMEM ? 512u : 256u;  // 2 accumulators x 128 columns (+ A hi/lo: 2 x 32*KB columns)
+  constexpr uint32_t TMEM_COLS = 512u;  // 2 accumulators x 128 columns + A hi/lo: 2 x 32*KB columns
   constexpr uint32_t COL_A_HI = 256u, COL_A_LO = 256u + 32u * KB;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS) : "memory");
@@ -209,24 +211,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== producer: one linear 32 KB bulk copy (TMA engine) per stage =====
     if (lane == 0) {
-      if constexpr (!A_TMEM) {
-        mbar_expect_tx(a_full, 2 * KB * TC_KBLOCK_BYTES);
-        for (int kb = 0; kb < KB; ++kb) {
-          tma_load_2d(sA_hi + kb * TC_KBLOCK_BYTES, &tm_qhi, a_full, kb * TC_BK, static_cast<int>(q0));
-          tma_load_2d(sA_lo + kb * TC_KBLOCK_BYTES, &tm_qlo, a_full, kb * TC_BK, static_cast<int>(q0));
-        }
-      }
       uint32_t stage = 0, phase = 0;
       for (uint32_t t = 0; t < n_tiles; ++t) {
-        const int row = static_cast<int>(n_begin + t * TC_BN);
+        const size_t tile = (n_begin / TC_BN) + t;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], 2 * TC_KBLOCK_BYTES);
-          unsigned char* dst = sB + stage * 2 * TC_KBLOCK_BYTES;
-          tma_load_2d(dst, &tm_bhi, &full[stage], kb * TC_BK, row);
-          tma_load_2d(dst + TC_KBLOCK_BYTES, &tm_blo, &full[stage], kb * TC_BK, row);
+          bulk_g2s(sB + stage * 2 * TC_KBLOCK_BYTES, a.b_tiled + (tile * KB + kb) * (2 * 4096), 2 * TC_KBLOCK_BYTES, &full[stage]);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -253,27 +246,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tc_fence_after();
           const uint64_t db_hi = umma_desc_sw128(sB + stage * 2 * TC_KBLOCK_BYTES);
           const uint64_t db_lo = umma_desc_sw128(sB + stage * 2 * TC_KBLOCK_BYTES + TC_KBLOCK_BYTES);
-          if constexpr (A_TMEM) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {  // A: +8 columns per UMMA_K; B: +2 descriptor units (32 bytes)
-              const uint64_t ko = static_cast<uint64_t>(2 * k);
-              const uint32_t a_hi = tmem_base + COL_A_HI + kb * TC_BK + k * 8;
-              const uint32_t a_lo = tmem_base + COL_A_LO + kb * TC_BK + k * 8;
-              umma_tf32_ts(tmem_c, a_hi, db_hi + ko, idesc, (kb | k) != 0);
-              umma_tf32_ts(tmem_c, a_hi, db_lo + ko, idesc, 1);
-              umma_tf32_ts(tmem_c, a_lo, db_hi + ko, idesc, 1);
-            }
-          }
-          else {
-            const uint64_t da_hi = umma_desc_sw128(sA_hi + kb * TC_KBLOCK_BYTES);
-            const uint64_t da_lo = umma_desc_sw128(sA_lo + kb * TC_KBLOCK_BYTES);
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = +2 in the descriptor's 16-byte units
-              const uint64_t ko = static_cast<uint64_t>(2 * k);
-              umma_tf32(tmem_c, da_hi + ko, db_hi + ko, idesc, (kb | k) != 0);
-              umma_tf32(tmem_c, da_hi + ko, db_lo + ko, idesc, 1);
-              umma_tf32(tmem_c, da_lo + ko, db_hi + ko, idesc, 1);
-            }
+          for (int k = 0; k < TC_BK / 8; ++k) {  // A: +8 TMEM columns per UMMA_K; B: +2 descriptor units (32 bytes)
+            const uint64_t ko = static_cast<uint64_t>(2 * k);
+            const uint32_t a_hi = tmem_base + COL_A_HI + kb * TC_BK + k * 8;
+            const uint32_t a_lo = tmem_base + COL_A_LO + kb * TC_BK + k * 8;
+            umma_tf32_ts(tmem_c, a_hi, db_hi + ko, idesc, (kb | k) != 0);
+            umma_tf32_ts(tmem_c, a_hi, db_lo + ko, idesc, 1);
+            umma_tf32_ts(tmem_c, a_lo, db_hi + ko, idesc, 1);
           }
           umma_commit(&empty[stage]);  // frees this B stage once the MMAs above have read it
           if (++stage == NSTAGE) {
@@ -294,28 +274,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t K = a.K;
     float* kb = s_kbest + r * TC_KP;
     for (uint32_t i = 0; i < TC_KP; ++i) kb[i] = G200_INF;
-    if constexpr (A_TMEM) {
-      // this thread's query row (hi, lo halves of -2q) -> tensor memory lane r, one column per K element
-      for (int half = 0; half < 2; ++half) {
-        const float* src = (half ? a.q_lo : a.q_hi) + static_cast<size_t>(min(q, a.N_query - 1)) * a.D;
-        for (int c = 0; c < KB; ++c) {
-          uint32_t v[32];
+    // this thread's query row (hi, lo halves of -2q) -> tensor memory lane r, one column per K element
+    for (int half = 0; half < 2; ++half) {
+      const float* src = (half ? a.q_lo : a.q_hi) + static_cast<size_t>(min(q, a.N_query - 1)) * a.D;
+      for (int c = 0; c < KB; ++c) {
+        uint32_t v[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 f = live ? reinterpret_cast<const float4*>(src + c * 32)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * j + 0] = __float_as_uint(f.x);
-            v[4 * j + 1] = __float_as_uint(f.y);
-            v[4 * j + 2] = __float_as_uint(f.z);
-            v[4 * j + 3] = __float_as_uint(f.w);
-          }
-          tmem_st32(tmem_base + (half ? COL_A_LO : COL_A_HI) + c * 32 + ((ew * 32u) << 16), v);
+        for (int j = 0; j < 8; ++j) {
+          const float4 f = live ? reinterpret_cast<const float4*>(src + c * 32)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * j + 0] = __float_as_uint(f.x);
+          v[4 * j + 1] = __float_as_uint(f.y);
+          v[4 * j + 2] = __float_as_uint(f.z);
+          v[4 * j + 3] = __float_as_uint(f.w);
         }
+        tmem_st32(tmem_base + (half ? COL_A_LO : COL_A_HI) + c * 32 + ((ew * 32u) << 16), v);
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
     }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_full);
     // error bound of the approximate score: 2^-13 * (|q|^2 + max |b|^2)
     const float margin = live ? ldexpf(a.qnorm[q] + __uint_as_float(*a.max_norm_bits), -13) : 0.f;
     float tau = G200_INF;  // K-th best approximate score so far (+inf until K rows were seen)
@@ -523,39 +501,6 @@ __global__ void __launch_bounds__(128) tc_fallback_kernel(const TcRerankArgs a)
 }
 
 // ---- host ---------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode()
-{
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
-}
-
-// [rows, D] fp32 row-major, box = {32 floats (128 B), 128 rows}, 128-byte swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint32_t D)
-{
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return set_error(GGNN_B200_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
-  const cuuint64_t dims[2] = {D, rows};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 4};
-  const cuuint32_t box[2] = {TC_BK, TC_BM};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(GGNN_B200_ERR_INVALID, "cuTensorMapEncodeTiled failed");
-  return 0;
-}
-
 struct TcWorkspace {
   float *b_hi, *b_lo, *bnorm, *q_hi, *q_lo, *qnorm;
   unsigned int* max_norm;
@@ -573,8 +518,9 @@ static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, u
     return p;
   };
   TcWorkspace w;
-  w.b_hi = reinterpret_cast<float*>(take(static_cast<size_t>(N) * D * 4));
-  w.b_lo = reinterpret_cast<float*>(take(static_cast<size_t>(N) * D * 4));
+  const size_t N_pad = (static_cast<size_t>(N) + TC_BN - 1) / TC_BN * TC_BN;
+  w.b_hi = reinterpret_cast<float*>(take(N_pad * D * 4 * 2));  // tile-major [hi | lo] records
+  w.b_lo = nullptr;
   w.bnorm = reinterpret_cast<float*>(take(static_cast<size_t>(N) * 4));
   w.q_hi = reinterpret_cast<float*>(take(static_cast<size_t>(Nq) * D * 4));
   w.q_lo = reinterpret_cast<float*>(take(static_cast<size_t>(Nq) * D * 4));
@@ -633,15 +579,10 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   cudaError_t e;
   if ((e = cudaMemsetAsync(w.max_norm, 0, 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset max_norm");
   if ((e = cudaMemsetAsync(w.cnt, 0, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset cnt");
-  tc_split_kernel<<<(N + 7) / 8, 256, 0, stream>>>(p.d_base, N, D, 1.0f, w.b_hi, w.b_lo, w.bnorm, w.max_norm);
-  tc_split_kernel<<<(Nq + 7) / 8, 256, 0, stream>>>(p.d_query, Nq, D, -2.0f, w.q_hi, w.q_lo, w.qnorm, nullptr);
+  const uint32_t N_pad = (N + TC_BN - 1) / TC_BN * TC_BN;
+  tc_split_kernel<<<(N_pad + 7) / 8, 256, 0, stream>>>(p.d_base, N, N_pad, D, 1.0f, 1, w.b_hi, nullptr, w.bnorm, w.max_norm);
+  tc_split_kernel<<<(Nq + 7) / 8, 256, 0, stream>>>(p.d_query, Nq, Nq, D, -2.0f, 0, w.q_hi, w.q_lo, w.qnorm, nullptr);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_split_kernel launch");
-
-  CUtensorMap tq_hi, tq_lo, tb_hi, tb_lo;
-  if (int rc = make_map(&tq_hi, w.q_hi, Nq, D)) return rc;
-  if (int rc = make_map(&tq_lo, w.q_lo, Nq, D)) return rc;
-  if (int rc = make_map(&tb_hi, w.b_hi, N, D)) return rc;
-  if (int rc = make_map(&tb_lo, w.b_lo, N, D)) return rc;
 
   const DeviceInfo& dev = device_info();
   const uint32_t q_tiles = (Nq + TC_BM - 1) / TC_BM;
@@ -662,15 +603,13 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ga.cnt = w.cnt;
   ga.q_hi = w.q_hi;
   ga.q_lo = w.q_lo;
+  ga.b_tiled = w.b_hi;
   ga.D = D;
-  const bool a_tmem = env_u32("GGNN_B200_BF_A_TMEM", 1) != 0;
-  const size_t smem_tail = TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
-  const size_t smem = (a_tmem ? static_cast<size_t>(TC_STAGES_TMEM) * 2 * TC_KBLOCK_BYTES
-                              : 2 * KB * TC_KBLOCK_BYTES + static_cast<size_t>(TC_STAGES) * 2 * TC_KBLOCK_BYTES) + smem_tail;
-  auto gemm = a_tmem ? tc_gemm_kernel<KB, true> : tc_gemm_kernel<KB, false>;
+  const size_t smem = static_cast<size_t>(TC_STAGES_TMEM) * 2 * TC_KBLOCK_BYTES + TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
+  auto gemm = tc_gemm_kernel<KB>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
-  gemm<<<dim3(q_tiles, splits), TC_THREADS, smem, stream>>>(tq_hi, tq_lo, tb_hi, tb_lo, ga);
+  gemm<<<dim3(q_tiles, splits), TC_THREADS, smem, stream>>>(ga);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_gemm_kernel launch");
 
   TcRerankArgs ra{};
