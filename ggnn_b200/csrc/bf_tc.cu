@@ -156,6 +156,8 @@ struct TcGemmArgs {
   const unsigned int* max_norm_bits;
   int32_t* cand;            // [N_query, cap]
   uint32_t* cnt;            // [N_query]
+  unsigned int* tau_g;      // [N_query] bits of the best known upper bound of each query's K-th best score,
+                            // shared by all base splits (atomicMin; scores are shifted to be >= 0)
 };
 
 // The 128-row query tile (hi and lo halves of -2q) lives in TENSOR MEMORY (columns 256..), written once per CTA with
@@ -295,49 +297,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
     __syncwarp();
     if (lane == 0) mbar_arrive(a_full);
     // error bound of the approximate score: 2^-13 * (|q|^2 + max |b|^2)
-    const float margin = live ? ldexpf(a.qnorm[q] + __uint_as_float(*a.max_norm_bits), -13) : 0.f;
-    float tau = G200_INF;  // K-th best approximate score so far (+inf until K rows were seen)
+    const float qn = live ? a.qnorm[q] : 0.f;
+    const float margin = live ? ldexpf(qn + __uint_as_float(*a.max_norm_bits), -13) : 0.f;
+    // tau: upper bound of the K-th best score (= |b|^2 - 2 q.b + |q|^2 >= 0 up to rounding): the K-th best of the rows
+    // this CTA has seen, tightened by what the other base splits of the same query have published in tau_g
+    float tau = G200_INF;
     for (uint32_t t = 0; t < n_tiles; ++t) {
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
       const uint32_t n0 = n_begin + t * TC_BN;
       // stage the tile's base norms (rows past the end never qualify)
       s_bnorm[acc * TC_BN + r] = (n0 + r < n_end) ? a.bnorm[n0 + r] : G200_INF;
+      if (live) tau = fminf(tau, __uint_as_float(__ldcg(&a.tau_g[q])));
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
       const float4* bn4 = reinterpret_cast<const float4*>(s_bnorm + acc * TC_BN);
+      bool improved = false;
 #pragma unroll 1
       for (int c = 0; c < TC_BN / 32; ++c) {
         float v[32];
         tmem_ld32(tmem_base + acc * TC_BN + c * 32 + ((ew * 32u) << 16), v);
-        const float thr = tau + margin;
+        const float thr = tau + margin - qn;  // compare the raw accumulator + |b|^2 against the shifted threshold
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 bn = bn4[c * 8 + j4];
           const float s0 = v[4 * j4 + 0] + bn.x, s1 = v[4 * j4 + 1] + bn.y;
           const float s2 = v[4 * j4 + 2] + bn.z, s3 = v[4 * j4 + 3] + bn.w;
-          if (fminf(fminf(s0, s1), fminf(s2, s3)) < thr) {  // rare after the first tiles
+          if (fminf(fminf(s0, s1), fminf(s2, s3)) < thr) {  // rare once tau is tight
             const float ss[4] = {s0, s1, s2, s3};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float s = ss[u];
+              const float s = fmaxf(ss[u] + qn, 0.f);
               if (s < tau + margin && live) {
                 const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
                 if (pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + pos] = static_cast<int32_t>(n0 + c * 32 + 4 * j4 + u);
-                if (s < tau) {  // insert into the row's sorted best list (ascending), K-th entry is tau
+                if (s < tau) {  // insert into the row's sorted best list (ascending); its K-th entry bounds tau
                   int i = static_cast<int>(K) - 1;
                   while (i > 0 && kb[i - 1] > s) {
                     kb[i] = kb[i - 1];
                     --i;
                   }
                   kb[i] = s;
-                  tau = kb[K - 1];
+                  if (kb[K - 1] < tau) {
+                    tau = kb[K - 1];
+                    improved = true;
+                  }
                 }
               }
             }
           }
         }
       }
+      if (improved) atomicMin(&a.tau_g[q], __float_as_uint(tau));  // non-negative floats order like their bit patterns
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -505,6 +516,7 @@ struct TcWorkspace {
   float *b_hi, *b_lo, *bnorm, *q_hi, *q_lo, *qnorm;
   unsigned int* max_norm;
   uint32_t* cnt;
+  unsigned int* tau_g;
   int32_t* cand;
   size_t total;
 };
@@ -527,6 +539,7 @@ static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, u
   w.qnorm = reinterpret_cast<float*>(take(static_cast<size_t>(Nq) * 4));
   w.max_norm = reinterpret_cast<unsigned int*>(take(1024));
   w.cnt = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(Nq) * 4));
+  w.tau_g = reinterpret_cast<unsigned int*>(take(static_cast<size_t>(Nq) * 4));
   w.cand = reinterpret_cast<int32_t*>(take(static_cast<size_t>(Nq) * cap * 4));
   w.total = off;
   return w;
@@ -579,6 +592,7 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   cudaError_t e;
   if ((e = cudaMemsetAsync(w.max_norm, 0, 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset max_norm");
   if ((e = cudaMemsetAsync(w.cnt, 0, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset cnt");
+  if ((e = cudaMemsetAsync(w.tau_g, 0x7f, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset tau");  // 0x7f7f7f7f = 3.4e38
   const uint32_t N_pad = (N + TC_BN - 1) / TC_BN * TC_BN;
   tc_split_kernel<<<(N_pad + 7) / 8, 256, 0, stream>>>(p.d_base, N, N_pad, D, 1.0f, 1, w.b_hi, nullptr, w.bnorm, w.max_norm);
   tc_split_kernel<<<(Nq + 7) / 8, 256, 0, stream>>>(p.d_query, Nq, Nq, D, -2.0f, 0, w.q_hi, w.q_lo, w.qnorm, nullptr);
@@ -601,6 +615,7 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ga.max_norm_bits = w.max_norm;
   ga.cand = w.cand;
   ga.cnt = w.cnt;
+  ga.tau_g = w.tau_g;
   ga.q_hi = w.q_hi;
   ga.q_lo = w.q_lo;
   ga.b_tiled = w.b_hi;
