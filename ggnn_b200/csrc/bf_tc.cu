@@ -29,7 +29,7 @@ constexpr int TC_BN = 128;     // base rows per tile (UMMA N)
 constexpr int TC_BK = 32;      // tf32 elements per shared-memory k-block (one 128-byte swizzle row)
 constexpr int TC_STAGES = 2;   // B ring depth (each stage = hi + lo k-block = 32 KB)
 constexpr int TC_KP = 32;      // max K of the tensor path (per-row best list in shared memory)
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;  // warps 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue (2 per TMEM lane quarter)
 constexpr uint32_t TC_KBLOCK_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
   constexpr int NSTAGE = TC_STAGES_TMEM;
   unsigned char* sB = smem;                                                       // [NSTAGE][hi 16 KB | lo 16 KB]
-  float* s_kbest = reinterpret_cast<float*>(sB + NSTAGE * 2 * TC_KBLOCK_BYTES);   // [128][TC_KP]
-  float* s_bnorm = s_kbest + TC_BM * TC_KP;                                       // [2][128]
+  float* s_kbest = reinterpret_cast<float*>(sB + NSTAGE * 2 * TC_KBLOCK_BYTES);   // [2 column halves][128][TC_KP]
+  float* s_bnorm = s_kbest + 2 * TC_BM * TC_KP;                                   // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bnorm + 2 * TC_BN);
   uint64_t* full = bars;                    // [NSTAGE]
   uint64_t* empty = bars + NSTAGE;          // [NSTAGE]
@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(a_full, 4);
+    mbar_init(a_full, 8);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 4);
+      mbar_init(&t_empty[i], 8);
     }
     mbar_fence_init();
   }
@@ -268,16 +268,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
     }
   }
   else if (warp >= 4) {
-    // ===== epilogue: one query row per thread =====
-    const int ew = warp - 4;                  // TMEM lane quarter == warp % 4
+    // ===== epilogue: one query row and one half of the tile's columns per thread =====
+    // warps 4..7 take columns [0,64), warps 8..11 columns [64,128) of every tile; each keeps its own best list
+    // (an extra base split in effect), the shared bound tau_g keeps both tight
+    const int ew = warp & 3;                  // TMEM lane quarter == warp % 4
+    const int ch = (warp - 4) >> 2;           // column half
     const uint32_t r = ew * 32 + lane;        // row in the tile
     const uint32_t q = q0 + r;
     const bool live = q < a.N_query;
     const uint32_t K = a.K;
-    float* kb = s_kbest + r * TC_KP;
+    float* kb = s_kbest + (ch * TC_BM + r) * TC_KP;
     for (uint32_t i = 0; i < TC_KP; ++i) kb[i] = G200_INF;
     // this thread's query row (hi, lo halves of -2q) -> tensor memory lane r, one column per K element
-    for (int half = 0; half < 2; ++half) {
+    {
+      const int half = ch;  // column-half-0 warps write the hi operand, column-half-1 warps the lo operand
       const float* src = (half ? a.q_lo : a.q_hi) + static_cast<size_t>(min(q, a.N_query - 1)) * a.D;
       for (int c = 0; c < KB; ++c) {
         uint32_t v[32];
@@ -306,15 +310,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
       const uint32_t n0 = n_begin + t * TC_BN;
       // stage the tile's base norms (rows past the end never qualify)
-      s_bnorm[acc * TC_BN + r] = (n0 + r < n_end) ? a.bnorm[n0 + r] : G200_INF;
+      if (ch == 0) s_bnorm[acc * TC_BN + r] = (n0 + r < n_end) ? a.bnorm[n0 + r] : G200_INF;
       if (live) tau = fminf(tau, __uint_as_float(__ldcg(&a.tau_g[q])));
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
       const float4* bn4 = reinterpret_cast<const float4*>(s_bnorm + acc * TC_BN);
       bool improved = false;
 #pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
+      for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
         float v[32];
         tmem_ld32(tmem_base + acc * TC_BN + c * 32 + ((ew * 32u) << 16), v);
         const float thr = tau + margin - qn;  // compare the raw accumulator + |b|^2 against the shifted threshold
@@ -620,7 +624,7 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ga.q_lo = w.q_lo;
   ga.b_tiled = w.b_hi;
   ga.D = D;
-  const size_t smem = static_cast<size_t>(TC_STAGES_TMEM) * 2 * TC_KBLOCK_BYTES + TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
+  const size_t smem = static_cast<size_t>(TC_STAGES_TMEM) * 2 * TC_KBLOCK_BYTES + 2 * TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
   auto gemm = tc_gemm_kernel<KB>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
