@@ -107,39 +107,64 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 // kb one contiguous 32 KB record [hi 16 KB | lo 16 KB] whose bytes are exactly the SWIZZLE_128B shared-memory image the
 // UMMA descriptor expects (16-byte chunk c of row r stored at chunk c ^ (r & 7)), so the GEMM streams B with ONE
 // linear 32 KB bulk copy per stage instead of 2 x 128 strided 128-byte row segments.  Rows past n_rows are zero.
+constexpr int TC_SPLIT_ROWS = 32;  // rows per CTA of tc_split_kernel (8 warps x 4 rows)
 __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ x, uint32_t n_rows, uint32_t n_rows_out,
                                                        uint32_t D, float scale, int tiled, float* __restrict__ hi,
                                                        float* __restrict__ lo, float* __restrict__ norms,
                                                        unsigned int* __restrict__ max_norm_bits)
 {
-  const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= n_rows_out) return;
+  __shared__ float s_max[8];
   const int lane = lane_id();
-  float acc = 0.f;
+  const int warp = threadIdx.x >> 5;
   const uint32_t KB = D / 32;
-  for (uint32_t d = lane; d < D; d += 32) {
-    const float v = row < n_rows ? x[static_cast<size_t>(row) * D + d] : 0.f;
-    acc = fmaf(v, v, acc);
-    const float s = v * scale;  // scale is a power of two: exact
-    const float h = __uint_as_float(__float_as_uint(s) & 0xffffe000u);
-    if (tiled) {
-      const uint32_t t = row >> 7, r = row & 127, kb = d >> 5, j = d & 31;
-      const size_t rec = (static_cast<size_t>(t) * KB + kb) * (2 * 4096);  // floats per 32 KB record
-      const uint32_t off = r * 32 + (((j >> 2) ^ (r & 7)) << 2) + (j & 3);
-      hi[rec + off] = h;           // `hi` is the record array; lo half follows at +4096 floats
-      hi[rec + 4096 + off] = s - h;
+  const uint32_t row0 = blockIdx.x * TC_SPLIT_ROWS + warp * 4;
+  const bool act = static_cast<uint32_t>(lane) < D / 4;  // one 16-byte chunk of the row per lane (D <= 128)
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t row = row0 + i;
+    v[i] = (act && row < n_rows) ? __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float wmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t row = row0 + i;
+    float acc = fmaf(v[i].w, v[i].w, fmaf(v[i].z, v[i].z, fmaf(v[i].y, v[i].y, v[i].x * v[i].x)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if (row < n_rows) {
+      if (lane == 0) norms[row] = acc;
+      wmax = fmaxf(wmax, acc);
     }
-    else {
-      hi[static_cast<size_t>(row) * D + d] = h;
-      lo[static_cast<size_t>(row) * D + d] = s - h;  // exact
+    if (row < n_rows_out && act) {
+      const float4 sv = make_float4(v[i].x * scale, v[i].y * scale, v[i].z * scale, v[i].w * scale);  // power-of-two scale: exact
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(sv.x) & 0xffffe000u);
+      h.y = __uint_as_float(__float_as_uint(sv.y) & 0xffffe000u);
+      h.z = __uint_as_float(__float_as_uint(sv.z) & 0xffffe000u);
+      h.w = __uint_as_float(__float_as_uint(sv.w) & 0xffffe000u);
+      l = make_float4(sv.x - h.x, sv.y - h.y, sv.z - h.z, sv.w - h.w);  // exact
+      if (tiled) {
+        const uint32_t t = row >> 7, r = row & 127, kb = lane >> 3, c = lane & 7;
+        float* rec = hi + (static_cast<size_t>(t) * KB + kb) * (2 * 4096);  // 32 KB record: [hi 16 KB | lo 16 KB]
+        const uint32_t off = r * 32 + ((c ^ (r & 7)) << 2);
+        *reinterpret_cast<float4*>(rec + off) = h;
+        *reinterpret_cast<float4*>(rec + 4096 + off) = l;
+      }
+      else {
+        reinterpret_cast<float4*>(hi + static_cast<size_t>(row) * D)[lane] = h;
+        reinterpret_cast<float4*>(lo + static_cast<size_t>(row) * D)[lane] = l;
+      }
     }
   }
-  if (row >= n_rows) return;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-  if (lane == 0) {
-    norms[row] = acc;
-    if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(acc));  // non-negative floats order like uints
+  if (max_norm_bits) {  // one atomic per CTA (non-negative floats order like their bit patterns)
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = s_max[0];
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, s_max[i]);
+      atomicMax(max_norm_bits, __float_as_uint(m));
+    }
   }
 }
 
@@ -163,6 +188,7 @@ struct TcGemmArgs {
 // The 128-row query tile (hi and lo halves of -2q) lives in TENSOR MEMORY (columns 256..), written once per CTA with
 // tcgen05.st; all shared memory goes to the B ring.
 constexpr int TC_STAGES_TMEM = 6;
+constexpr uint32_t TC_CHUNK = 8;
 
 template <int KB>  // k-blocks: D = 32*KB
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs a)
@@ -306,6 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
     // tau: upper bound of the K-th best score (= |b|^2 - 2 q.b + |q|^2 >= 0 up to rounding): the K-th best of the rows
     // this CTA has seen, tightened by what the other base splits of the same query have published in tau_g
     float tau = G200_INF;
+    uint32_t c_pos = 0, c_left = 0;  // this thread's current chunk of candidate slots
     for (uint32_t t = 0; t < n_tiles; ++t) {
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
       const uint32_t n0 = n_begin + t * TC_BN;
@@ -333,8 +360,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
             for (int u = 0; u < 4; ++u) {
               const float s = fmaxf(ss[u] + qn, 0.f);
               if (s < tau + margin && live) {
-                const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
-                if (pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + pos] = static_cast<int32_t>(n0 + c * 32 + 4 * j4 + u);
+                // candidate slots are handed out in chunks of TC_CHUNK per (query, list): one returning atomic per chunk
+                if (c_left == 0) {
+                  c_pos = atomicAdd(&a.cnt[q], TC_CHUNK);
+                  c_left = TC_CHUNK;
+                }
+                if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + c * 32 + 4 * j4 + u);
+                ++c_pos;
+                --c_left;
                 if (s < tau) {  // insert into the row's sorted best list (ascending); its K-th entry bounds tau
                   int i = static_cast<int>(K) - 1;
                   while (i > 0 && kb[i - 1] > s) {
@@ -357,6 +390,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
     }
+    // unused slots of the last chunk hold no candidate
+    for (; c_left > 0; --c_left, ++c_pos)
+      if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = -1;
   }
   __syncthreads();
   if (warp == 2) {
@@ -460,9 +496,10 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const TcRerankArgs a)
   const uint32_t K = p.KQuery;
   for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
     const int nb = min(32u, cnt - c0);
-    const int id = (lane < nb) ? a.cand[static_cast<size_t>(n) * a.cap + c0 + lane] : 0;
+    const int cid = (lane < nb) ? a.cand[static_cast<size_t>(n) * a.cap + c0 + lane] : -1;  // -1: unused slot of a chunk
+    const int id = max(cid, 0);
     const float d = stage_and_dist<true, D32, 1>(ws, qv, p.d_base, id, 0, nb);
-    unsigned rem = nb >= 32 ? FULL : ((1u << nb) - 1u);
+    unsigned rem = __ballot_sync(FULL, cid >= 0);
     while (true) {
       float wd;
       int wi;
@@ -598,8 +635,8 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   if ((e = cudaMemsetAsync(w.cnt, 0, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset cnt");
   if ((e = cudaMemsetAsync(w.tau_g, 0x7f, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset tau");  // 0x7f7f7f7f = 3.4e38
   const uint32_t N_pad = (N + TC_BN - 1) / TC_BN * TC_BN;
-  tc_split_kernel<<<(N_pad + 7) / 8, 256, 0, stream>>>(p.d_base, N, N_pad, D, 1.0f, 1, w.b_hi, nullptr, w.bnorm, w.max_norm);
-  tc_split_kernel<<<(Nq + 7) / 8, 256, 0, stream>>>(p.d_query, Nq, Nq, D, -2.0f, 0, w.q_hi, w.q_lo, w.qnorm, nullptr);
+  tc_split_kernel<<<(N_pad + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, 256, 0, stream>>>(p.d_base, N, N_pad, D, 1.0f, 1, w.b_hi, nullptr, w.bnorm, w.max_norm);
+  tc_split_kernel<<<(Nq + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, 256, 0, stream>>>(p.d_query, Nq, Nq, D, -2.0f, 0, w.q_hi, w.q_lo, w.qnorm, nullptr);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_split_kernel launch");
 
   const DeviceInfo& dev = device_info();
