@@ -92,6 +92,21 @@ class _Shard:
         self.graph = None         # Graph
 
 
+class QueryFuture:
+    """Handle of a query enqueued by GGNN.query_async()."""
+
+    def __init__(self, events, ids, dists):
+        self._events, self._ids, self._dists = events, ids, dists
+
+    def done(self):
+        return all(e.query() for e in self._events)
+
+    def result(self):
+        for e in self._events:
+            e.synchronize()
+        return self._ids, self._dists
+
+
 class GGNN:
     """Drop-in for ggnn.GGNN (include/ggnn/base/ggnn.cuh:41-182, nanobind.cu:184-267)."""
 
@@ -109,6 +124,8 @@ class GGNN:
         self._measure = None
         self._work_counters = {}
         self._base_dtype = torch.float32
+        self._host_streams = {}
+        self._host_rr = 0
 
     # ---- configuration (ggnn.cu:53-60, 420-454) ----
     def set_working_directory(self, path):
@@ -277,6 +294,9 @@ class GGNN:
         n_gpus = len(self._gpus)
         if self._results_on_gpu and n_gpus > 1:
             raise RuntimeError("Returning query results on GPU is only possible when using a single GPU.")
+        if n_gpus == 1 and not self._results_on_gpu and not query.is_cuda:
+            chunks = int(os.environ.get("GGNN_B200_QUERY_CHUNKS", "0")) or (2 if query.shape[0] >= 4096 else 1)
+            return self._enqueue_host_query(query, k_query, tau_query, max_iterations, measure, chunks).result()
         per_gpu = []
         for gi in range(n_gpus):
             dev = self._shards[gi * self._spg].device
@@ -302,6 +322,53 @@ class GGNN:
         if self._results_on_gpu:
             return ids, dists
         return ids.cpu(), dists.cpu()
+
+    def query_async(self, query, k_query, tau_query, max_iterations=400, measure=DistanceMeasure.Euclidean):
+        """query() for a HOST query tensor on a single GPU without waiting: the host->device copy, the traversal and
+        the device->host copy of the results are enqueued on one of this instance's own streams; .result() of the
+        returned QueryFuture waits for them and hands out (ids, dists) in pinned host memory.  Several batches may be
+        in flight at once: their copies overlap the other batches' kernels, and the SMs a batch's last long queries
+        leave idle are filled by the next batch.  (The reference's query is synchronous only: ggnn.cu:506-551.)"""
+        if not self._shards or self._shards[0].graph is None:
+            raise RuntimeError("There is no graph to query.")
+        query = _as_tensor(query, "query")
+        if query.dtype != getattr(self, "_base_dtype", torch.float32):
+            raise ValueError("query data type has to match base data type")
+        if query.shape[1] != self._base.shape[1]:
+            raise ValueError("query dimension does not match the base")
+        if len(self._gpus) != 1 or query.is_cuda:
+            raise RuntimeError("query_async takes a host tensor and a single GPU")
+        return self._enqueue_host_query(query, int(k_query), tau_query, max_iterations, measure, 1)
+
+    def _enqueue_host_query(self, query, k_query, tau_query, max_iterations, measure, n_chunks):
+        dev = self._shards[0].device
+        Nq = query.shape[0]
+        if dev not in self._host_streams:
+            self._host_streams[dev] = [torch.cuda.Stream(dev) for _ in range(4)]
+        streams = self._host_streams[dev]
+        out_i = torch.empty((Nq, k_query), dtype=torch.int32, pin_memory=True)
+        out_d = torch.empty((Nq, k_query), dtype=torch.float32, pin_memory=True)
+        n_chunks = max(1, min(int(n_chunks), len(streams), max(1, Nq)))
+        bounds = [Nq * c // n_chunks for c in range(n_chunks + 1)]
+        events = []
+        with torch.cuda.device(dev):
+            start = torch.cuda.current_stream(dev).record_event()  # after whatever the caller enqueued before
+            for c in range(n_chunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                if hi == lo:
+                    continue
+                st = streams[self._host_rr % len(streams)]
+                self._host_rr += 1
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    q_dev = query[lo:hi].to(dev, non_blocking=True)
+                    if q_dev.dtype == torch.uint8:
+                        q_dev = q_dev.float()
+                    ids, dists = self._query_device(0, q_dev.contiguous(), k_query, tau_query, max_iterations, measure)
+                    out_i[lo:hi].copy_(ids, non_blocking=True)
+                    out_d[lo:hi].copy_(dists, non_blocking=True)
+                    events.append(st.record_event())
+        return QueryFuture(events, out_i, out_d)
 
     def bf_query(self, query, k_gt=100, measure=DistanceMeasure.Euclidean):
         if self._base is None:

@@ -454,3 +454,28 @@ def test_uint8_base_vectors_match_oracle_on_widened_values():
                          gr.nn1_stats.cpu().numpy(), 10, 0.64, 400)
     assert np.array_equal(ids.numpy(), o_ids) and np.array_equal(dists.numpy(), o_d)
     assert float(dists.numpy()[0, 0]) == float(int(dists.numpy()[0, 0]))  # integer-valued squared distances
+
+
+def test_host_query_paths_agree_with_device_query(monkeypatch):
+    """query() on a host tensor (chunks pipelined over internal streams) and query_async() (several batches in
+    flight) return exactly what the device-resident query returns (every query is independent: ggnn.cu:506-551)"""
+    base, query = gen_data(20000, 5000, 64, seed=5)
+    g = ggnn.GGNN()
+    g.set_base(torch.from_numpy(base))
+    g.build(24, 0.5)
+    g.set_return_results_on_gpu(True)
+    ref_i, ref_d = g.query(torch.from_numpy(query).cuda(), 10, 0.5, 200)
+    g.set_return_results_on_gpu(False)
+    q_pinned = torch.from_numpy(query).pin_memory()
+    for chunks in ("1", "2", "3"):
+        monkeypatch.setenv("GGNN_B200_QUERY_CHUNKS", chunks)
+        for q in (q_pinned, query):  # pinned tensor and pageable numpy array
+            i, d = g.query(q, 10, 0.5, 200)
+            assert not i.is_cuda and torch.equal(i, ref_i.cpu()) and torch.equal(d, ref_d.cpu())
+    futs = [g.query_async(q_pinned[o:o + 2500], 10, 0.5, 200) for o in (0, 2500)] * 3
+    for n, f in enumerate(futs):
+        i, d = f.result()
+        o = (0, 2500)[n % 2]
+        assert f.done() and torch.equal(i, ref_i[o:o + 2500].cpu()) and torch.equal(d, ref_d[o:o + 2500].cpu())
+    with pytest.raises(RuntimeError):
+        g.query_async(q_pinned.cuda(), 10, 0.5, 200)
