@@ -184,10 +184,16 @@ def run_ours(a):
     def local_query(q):
         return idx.query(q, K, a.tau_query, a.max_iterations)
 
-    def step_device():
+    # N > 1: every pipeline (CUDA stream) gets its own NCCL communicator and its own receive buffer for the broadcast
+    # query batch, so the collectives of batches in flight neither serialise on one communicator nor alias
+    n_pipes = max(1, a.streams)
+    groups = [dist.new_group(backend="nccl") for _ in range(n_pipes)] if world > 1 else [None] * n_pipes
+    q_bufs = [query if (rank == 0 or world == 1) else torch.empty_like(query) for _ in range(n_pipes)]
+
+    def step_device(pipe=0):
         if world == 1:
             return local_query(query)
-        return gd.distributed_query(local_query, gd.gpu_merge, query, K, a.n_base, broadcast=True)
+        return gd.distributed_query(local_query, gd.gpu_merge, q_bufs[pipe], K, a.n_base, group=groups[pipe], broadcast=True)
 
     # ground truth + recall (untimed): exact brute force on every shard, merged the same way
     def bf_local(q):
@@ -225,7 +231,7 @@ def run_ours(a):
     # alternating CUDA streams, so the next batch's CTAs fill the SMs that the previous batch's last, long
     # queries leave idle (the kernel's tail is one query latency).  --streams 1 serialises the batches.
     sampler = ClockSampler(local)
-    n_streams = max(1, a.streams) if world == 1 else 1
+    n_streams = n_pipes
     streams = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else [torch.cuda.current_stream(dev)]
     outs = [None] * n_streams
 
@@ -233,7 +239,7 @@ def run_ours(a):
         for s in range(n):
             st = streams[s % n_streams]
             with torch.cuda.stream(st):
-                outs[s % n_streams] = step_device()
+                outs[s % n_streams] = step_device(s % n_streams)
 
     run_steps(a.warmup)
     torch.cuda.synchronize()
@@ -308,12 +314,48 @@ def run_ours(a):
         e2e_ms, e2e_depth = (time.perf_counter() - t0) * 1e3, a.e2e_depth
         r_sync = step_e2e()
         assert torch.equal(r_async[0], r_sync[0]) and torch.equal(r_async[1], r_sync[1]), "async and sync results differ"
-    times = torch.tensor([total_ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    elif world > 1 and a.e2e_depth > 1 and n_streams > 1:
+        # N > 1: one batch in flight per pipeline (stream + communicator).  Rank 0 copies the batch host->device, it is
+        # broadcast, every rank searches its shard, the lists are gathered and merged, rank 0 copies the result back.
+        idx.set_return_results_on_gpu(True)
+        qd = [torch.empty_like(query) for _ in range(n_streams)]
+        pin_i = [torch.empty((a.n_query, K), dtype=torch.int32, pin_memory=True) for _ in range(n_streams)]
+        pin_d = [torch.empty((a.n_query, K), dtype=torch.float32, pin_memory=True) for _ in range(n_streams)]
+        evs = [None] * n_streams
+
+        def run_async(n):
+            for s_ in range(n):
+                pipe = s_ % n_streams
+                if evs[pipe] is not None:
+                    evs[pipe].synchronize()  # the step that used this pipeline's buffers has delivered its result
+                with torch.cuda.stream(streams[pipe]):
+                    if rank == 0:
+                        qd[pipe].copy_(q_host, non_blocking=True)
+                    r = gd.distributed_query(local_query, gd.gpu_merge, qd[pipe], K, a.n_base, group=groups[pipe], broadcast=True)
+                    if rank == 0:
+                        pin_i[pipe].copy_(r[0], non_blocking=True)
+                        pin_d[pipe].copy_(r[1], non_blocking=True)
+                    evs[pipe] = streams[pipe].record_event()
+            for e in evs:
+                if e is not None:
+                    e.synchronize()
+        run_async(max(2, a.warmup // 2))
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_async(a.steps)
+        torch.cuda.synchronize()
+        e2e_ms, e2e_depth = (time.perf_counter() - t0) * 1e3, n_streams
+        if rank == 0:
+            r_sync = step_e2e()
+            last = (a.steps - 1) % n_streams
+            assert torch.equal(pin_i[last], r_sync[0]) and torch.equal(pin_d[last], r_sync[1]), "async and sync results differ"
+        else:
+            step_e2e()
+    times = torch.tensor([total_ms, e2e_ms, kernel_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kernel_ms = times.tolist()
-    if world > 1:
-        e2e_sync_ms = e2e_ms
+    total_ms, e2e_ms, kernel_ms, e2e_sync_ms = times.tolist()
 
     if rank != 0:
         if world > 1:
@@ -344,7 +386,9 @@ def run_ours(a):
         "recall_at_10": rec,
         "e2e": {"value": e2e_qps * shards, "unit": "queries/s" if shards == 1 else "queries/s x shards searched",
                 "h2d_bytes_per_step": a.n_query * a.dim * 4, "d2h_bytes_per_step": a.n_query * K * 8,
-                "mode": (f"GGNN.query_async(), {e2e_depth} batches in flight" if e2e_depth > 1 else "GGNN.query(), one synchronous call per step"),
+                "mode": ((f"GGNN.query_async(), {e2e_depth} batches in flight" if shards == 1 else
+                          f"{e2e_depth} batches in flight: pinned H2D on rank 0, broadcast, per-shard query, all_gather, merge, D2H on rank 0")
+                         if e2e_depth > 1 else "one synchronous call per step"),
                 "sync_value": a.n_query / (e2e_sync_ms / a.steps * 1e-3) * shards},
         "gpu_launches": a.steps * (1 + (1 if shards > 1 else 0)),
         "clocks": clocks,
@@ -354,7 +398,7 @@ def run_ours(a):
                      "pops_per_query": n_iter / a.n_query, "dists_per_query": n_dist / a.n_query},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -412,7 +456,7 @@ def run_reference(a):
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     base_line = {"impl": "reference", "metric": "queries/sec @ recall@10", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup}
     if not os.path.exists(drv):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built (bash oracle/build_ref.sh needs /root/reference)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built (bash oracle/build_ref.sh needs /root/reference)"})
         return
     shards = a.gpus
     wd = os.path.join("/tmp", f"ggnn_ref_bench_{os.getpid()}")
@@ -434,7 +478,7 @@ def run_reference(a):
             f"bf={a.k_query if shards == 1 else 0}", "dump=1", f"gpus={shards}", f"shard={a.n_base}"]
     p = subprocess.run(args, capture_output=True, text=True)
     if p.returncode != 0:
-        print(json.dumps({"impl": "reference", "unavailable": f"ref_driver rc={p.returncode}: {p.stderr[-300:]}"}))
+        emit({"impl": "reference", "unavailable": f"ref_driver rc={p.returncode}: {p.stderr[-300:]}"})
         return
     r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
     e2e = r["query_e2e_ms"][a.warmup:]
@@ -467,7 +511,20 @@ def run_reference(a):
                                    "kernels (unmodified sources, compiled for sm_100a) through ggnn::GGNN::query on "
                                    "pinned host buffers; host threads = 1 per GPU (+ CPU merge threads for N>1)"},
     })
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
@@ -490,4 +547,9 @@ def main():
 
 
 if __name__ == "__main__":
+    # the contract is ONE JSON line on stdout: libraries that write to file descriptor 1 themselves (NCCL prints its
+    # version there when a communicator is created) are sent to stderr; only emit() writes to the real stdout
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
