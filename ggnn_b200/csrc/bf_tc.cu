@@ -101,6 +101,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4])
+{
+  uint32_t r[4];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- stage 1: split + norms ---------------------------------------------------------------------
 // one warp per row; out rows padded with zeros up to n_rows_pad (TMA never reads past them anyway)
 // tiled != 0 (base operand): output is tile-major and PRE-SWIZZLED -- for every 128-row tile t and 32-column k-block
@@ -344,42 +357,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
       tc_fence_after();
       const float4* bn4 = reinterpret_cast<const float4*>(s_bnorm + acc * TC_BN);
       bool improved = false;
+      // pass 1, branch-free: which groups of 4 columns hold a score below the threshold?  (compare the raw
+      // accumulator + |b|^2 against the shifted threshold)
+      const float thr = tau + margin - qn;
+      uint32_t m = 0;
 #pragma unroll 1
-      for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * ch + cc;
         float v[32];
         tmem_ld32(tmem_base + acc * TC_BN + c * 32 + ((ew * 32u) << 16), v);
-        const float thr = tau + margin - qn;  // compare the raw accumulator + |b|^2 against the shifted threshold
+        uint32_t mc = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 bn = bn4[c * 8 + j4];
           const float s0 = v[4 * j4 + 0] + bn.x, s1 = v[4 * j4 + 1] + bn.y;
           const float s2 = v[4 * j4 + 2] + bn.z, s3 = v[4 * j4 + 3] + bn.w;
-          if (fminf(fminf(s0, s1), fminf(s2, s3)) < thr) {  // rare once tau is tight
-            const float ss[4] = {s0, s1, s2, s3};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float s = fmaxf(ss[u] + qn, 0.f);
-              if (s < tau + margin && live) {
-                // candidate slots are handed out in chunks of TC_CHUNK per (query, list): one returning atomic per chunk
-                if (c_left == 0) {
-                  c_pos = atomicAdd(&a.cnt[q], TC_CHUNK);
-                  c_left = TC_CHUNK;
-                }
-                if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + c * 32 + 4 * j4 + u);
-                ++c_pos;
-                --c_left;
-                if (s < tau) {  // insert into the row's sorted best list (ascending); its K-th entry bounds tau
-                  int i = static_cast<int>(K) - 1;
-                  while (i > 0 && kb[i - 1] > s) {
-                    kb[i] = kb[i - 1];
-                    --i;
-                  }
-                  kb[i] = s;
-                  if (kb[K - 1] < tau) {
-                    tau = kb[K - 1];
-                    improved = true;
-                  }
-                }
+          mc |= (fminf(fminf(s0, s1), fminf(s2, s3)) < thr ? 1u : 0u) << j4;
+        }
+        m |= mc << (8 * cc);
+      }
+      if (!live) m = 0;  // rows past the last query
+      // pass 2, rare once tau is tight: ONE copy of the candidate / insertion code.  The warp walks the union of the
+      // lanes' group masks; the 4 columns of a group are re-read from tensor memory (warp-wide, 4 registers).
+      for (uint32_t um = __reduce_or_sync(FULL, m); um; um &= um - 1) {
+        const int g = __ffs(um) - 1;                   // group within this warp's column half
+        const int col = 2 * ch * 32 + 4 * g;           // first of its 4 columns in the tile
+        float w[4];
+        tmem_ld4(tmem_base + acc * TC_BN + col + ((ew * 32u) << 16), w);
+        if (!((m >> g) & 1u)) continue;
+        const float4 bn = bn4[col >> 2];
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+          const float acc_u = u == 0 ? w[0] : (u == 1 ? w[1] : (u == 2 ? w[2] : w[3]));
+          const float bn_u = u == 0 ? bn.x : (u == 1 ? bn.y : (u == 2 ? bn.z : bn.w));
+          const float s = fmaxf(acc_u + bn_u + qn, 0.f);
+          if (s < tau + margin) {
+            // candidate slots are handed out in chunks of TC_CHUNK per (query, list): one returning atomic per chunk
+            if (c_left == 0) {
+              c_pos = atomicAdd(&a.cnt[q], TC_CHUNK);
+              c_left = TC_CHUNK;
+            }
+            if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + col + u);
+            ++c_pos;
+            --c_left;
+            if (s < tau) {  // insert into the row's sorted best list (ascending); its K-th entry bounds tau
+              int i = static_cast<int>(K) - 1;
+              while (i > 0 && kb[i - 1] > s) {
+                kb[i] = kb[i - 1];
+                --i;
+              }
+              kb[i] = s;
+              if (kb[K - 1] < tau) {
+                tau = kb[K - 1];
+                improved = true;
               }
             }
           }
