@@ -21,6 +21,8 @@
 #include "../../include/ggnn_b200.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <vector>
 
 namespace g200 {
 
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
 struct TcGemmArgs {
   uint32_t N_base, N_query, K, cap;
   uint32_t rows_per_split;  // multiple of TC_BN
+  unsigned int* pub;        // [N_query][2 * splits][K] published best lists (merger warp), or nullptr
   const float* bnorm;       // [N_base]
   const float* qnorm;       // [N_query]
   const float* q_hi;        // [N_query, D] hi / lo halves of -2*query (row-major)
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
   uint64_t* t_full = a_full + 1;            // [2]
   uint64_t* t_empty = t_full + 2;           // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(t_empty + 2);
+  volatile uint32_t* s_done = s_tmem + 1;  // epilogue warps that have finished
 
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
@@ -233,6 +237,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    *s_done = 0;
     mbar_init(a_full, 8);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
@@ -303,6 +308,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
           }
         }
         umma_commit(&t_full[acc]);  // accumulator complete
+      }
+    }
+  }
+  else if (warp == 3) {
+    // ===== merger: tightens the shared bound tau_g of this CTA's 128 queries while the tiles stream =====
+    // A list's K-th entry only bounds the K-th best of ITS rows (1/n_lists of the base), so the minimum over lists is
+    // about the K*n_lists-th best overall.  The K-th smallest entry of the UNION of the published lists (distinct rows)
+    // is the K-th best of everything seen so far.  Lists only ever decrease entry-wise, so a snapshot torn by
+    // concurrent updates undercounts and the bound stays valid.  Non-negative floats are compared as bit patterns.
+    if (a.pub != nullptr) {
+      const uint32_t n_lists = gridDim.y * 2, K = a.K;
+      const uint32_t M = min(n_lists * K, 512u);  // at most 16 values per lane (a prefix of the lists is still valid)
+      bool run = true;
+      while (run) {
+#pragma unroll 1
+        for (uint32_t r = 0; r < TC_BM; ++r) {
+          const uint32_t q = q0 + r;
+          if (*s_done >= 8u || q >= a.N_query) {
+            run = *s_done < 8u;
+            break;
+          }
+          const unsigned int* src = a.pub + static_cast<size_t>(q) * n_lists * K;
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = lane + 32 * j < M ? __ldcg(src + lane + 32 * j) : 0x7f7f7f7fu;
+          uint32_t x = 0;  // smallest x with count(v <= x) >= K, from the top bit down; the low 12 bits stay at 1
+#pragma unroll 1
+          for (int b = 30; b >= 12; --b) {
+            const uint32_t y = x | ((1u << b) - 1u);
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) c += v[j] <= y;
+            c = __reduce_add_sync(FULL, c);
+            if (static_cast<uint32_t>(c) < K) x |= 1u << b;
+          }
+          x |= 4095u;
+          if (lane == 0 && x < __ldcg(&a.tau_g[q])) atomicMin(&a.tau_g[q], x);
+          __nanosleep(500);
+        }
       }
     }
   }
@@ -415,11 +459,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
           }
         }
       }
-      if (improved) atomicMin(&a.tau_g[q], __float_as_uint(tau));  // non-negative floats order like their bit patterns
+      if (improved) {
+        atomicMin(&a.tau_g[q], __float_as_uint(tau));  // non-negative floats order like their bit patterns
+        if (a.pub != nullptr) {
+          unsigned int* dst = a.pub + (static_cast<size_t>(q) * (gridDim.y * 2) + blockIdx.y * 2 + ch) * K;
+          for (uint32_t i = 0; i < K; ++i) dst[i] = __float_as_uint(kb[i]);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
     }
+    if (lane == 0) atomicAdd(const_cast<uint32_t*>(s_done), 1u);
     // unused slots of the last chunk hold no candidate
     for (; c_left > 0; --c_left, ++c_pos)
       if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = -1;
@@ -588,9 +639,11 @@ struct TcWorkspace {
   unsigned int* max_norm;
   uint32_t* cnt;
   unsigned int* tau_g;
+  unsigned int* pub;
   int32_t* cand;
   size_t total;
 };
+constexpr uint32_t TC_MAX_SPLITS = 32;  // 64 published best lists per query
 static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, uint32_t cap)
 {
   char* b = static_cast<char*>(basep);
@@ -611,6 +664,7 @@ static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, u
   w.max_norm = reinterpret_cast<unsigned int*>(take(1024));
   w.cnt = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(Nq) * 4));
   w.tau_g = reinterpret_cast<unsigned int*>(take(static_cast<size_t>(Nq) * 4));
+  w.pub = reinterpret_cast<unsigned int*>(take(static_cast<size_t>(Nq) * 2 * TC_MAX_SPLITS * TC_KP * 4));
   w.cand = reinterpret_cast<int32_t*>(take(static_cast<size_t>(Nq) * cap * 4));
   w.total = off;
   return w;
@@ -632,8 +686,8 @@ static uint32_t tc_cap(uint32_t Nq)
 static uint32_t tc_pick_splits(uint32_t q_tiles, uint32_t n_tiles, uint32_t num_sms, uint32_t cap)
 {
   const uint32_t forced = env_u32("GGNN_B200_BF_SPLITS", 0);
-  const uint32_t s_max = std::max(1u, std::min(n_tiles, cap / TC_CAND_PER_SPLIT));
-  if (forced) return std::max(1u, std::min(forced, n_tiles));
+  const uint32_t s_max = std::max(1u, std::min(std::min(n_tiles, TC_MAX_SPLITS), cap / TC_CAND_PER_SPLIT));
+  if (forced) return std::max(1u, std::min(std::min(forced, TC_MAX_SPLITS), n_tiles));
   uint32_t best = 1;
   double best_score = -1.0;
   for (uint32_t s = 1; s <= s_max; ++s) {
@@ -687,6 +741,9 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ga.cand = w.cand;
   ga.cnt = w.cnt;
   ga.tau_g = w.tau_g;
+  ga.pub = env_u32("GGNN_B200_BF_MERGER", 1) ? w.pub : nullptr;
+  if (ga.pub && (e = cudaMemsetAsync(w.pub, 0x7f, static_cast<size_t>(Nq) * 2 * splits * p.KQuery * 4, stream)) != cudaSuccess)
+    return set_cuda_error(e, "memset pub");
   ga.q_hi = w.q_hi;
   ga.q_lo = w.q_lo;
   ga.b_tiled = w.b_hi;
@@ -711,6 +768,20 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
     return set_cuda_error(e, "cudaFuncSetAttribute(tc_rerank_kernel)");
   rr<<<(Nq + 3) / 4, 128, rsmem, stream>>>(ra);
   tc_fallback_kernel<<<(Nq + 3) / 4, 128, 4 * D * 4, stream>>>(ra);
+  if (env_u32("GGNN_B200_BF_DEBUG", 0)) {  // diagnostics only: candidate slots handed out per query
+    std::vector<uint32_t> h(Nq);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), w.cnt, static_cast<size_t>(Nq) * 4, cudaMemcpyDeviceToHost);
+    uint64_t sum = 0;
+    uint32_t mx = 0, over = 0;
+    for (uint32_t c : h) {
+      sum += c;
+      mx = std::max(mx, c);
+      over += c > cap;
+    }
+    fprintf(stderr, "[bf_tc] splits %u q_tiles %u cap %u: candidate slots/query mean %.1f max %u, overflowed %u\n", splits,
+            q_tiles, cap, static_cast<double>(sum) / Nq, mx, over);
+  }
   return set_cuda_error(cudaGetLastError(), "tc_rerank / tc_fallback launch");
 }
 
