@@ -5,8 +5,8 @@ shard, searches every shard with the same query batch and merges the per-shard t
 (src/ggnn/base/ggnn.cu:154-203, 278-330; src/ggnn/base/result_merger.cpp:51-149).  It does all of that
 in one process with one host thread per GPU, D2H copies and a CPU heap merge.  Here rank r owns GPU r
 and global shards [r*spg, (r+1)*spg); the only exchange is the natural one: the query batch is
-broadcast from rank 0 and the per-rank sorted [Nq, K] (id, dist) lists are all-gathered (Nq*K*8 bytes per
-rank) and merged by one kernel (ggnn_b200_merge_topk) -- no collective on the data path of the search.
+broadcast from rank 0 and the per-rank sorted [Nq, K] (id, dist) lists are all-gathered (one collective, Nq*K*8
+bytes per rank) and merged by one kernel (ggnn_b200_merge_topk) -- no collective on the data path of the search.
 """
 import torch
 import torch.distributed as dist
@@ -42,11 +42,11 @@ def distributed_query(local_query_fn, merge_fn, query, k, rows_per_rank, group=N
     ids, dists = local_query_fn(query)
     if world == 1:
         return ids, dists
-    all_i = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-    all_d = torch.empty((world,) + tuple(dists.shape), dtype=dists.dtype, device=dists.device)
-    dist.all_gather(list(all_i.unbind(0)), ids.contiguous(), group=group)
-    dist.all_gather(list(all_d.unbind(0)), dists.contiguous(), group=group)
-    return merge_fn(all_i, all_d, rows_per_rank)
+    # ONE collective per batch: (ids, dists) travel packed as [2, Nq, K] 32-bit words per rank
+    packed = torch.stack((ids.contiguous(), dists.contiguous().view(torch.int32)))
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int32, device=ids.device)
+    dist.all_gather(list(gathered.unbind(0)), packed, group=group)
+    return merge_fn(gathered[:, 0], gathered[:, 1].view(torch.float32), rows_per_rank)
 
 
 def gpu_merge(all_ids, all_dists, id_offset_per_list, k=None):
@@ -61,7 +61,10 @@ def gpu_merge(all_ids, all_dists, id_offset_per_list, k=None):
     out_i = torch.empty((Nq, k), dtype=torch.int32, device=dev)
     out_d = torch.empty((Nq, k), dtype=torch.float32, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    # the W lists may be strided views of one gathered buffer: rows of a list must be dense, lists any distance apart
+    if all_ids.stride() != all_dists.stride() or tuple(all_ids.stride()[1:]) != (K_in, 1):
+        all_ids, all_dists = all_ids.contiguous(), all_dists.contiguous()
     _lib.check(_lib.lib().ggnn_b200_merge_topk(C.c_void_p(all_ids.data_ptr()), C.c_void_p(all_dists.data_ptr()), W,
-                                               Nq * K_in, K_in, K_in, Nq, k, int(id_offset_per_list),
+                                               all_ids.stride(0), K_in, K_in, Nq, k, int(id_offset_per_list),
                                                C.c_void_p(out_i.data_ptr()), C.c_void_p(out_d.data_ptr()), stream))
     return out_i, out_d
