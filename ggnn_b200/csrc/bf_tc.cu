@@ -2,15 +2,23 @@
 //
 // bf_query really is a contraction: ||b-q||^2 = ||b||^2 + (-2q).b + ||q||^2.  Three stages:
 //   1. split   : one streaming pass writes hi/lo TF32 halves of base and (-2)*query (x = hi + lo, hi = x with the
-//                13 low mantissa bits cleared) and the row norms.
-//   2. gemm    : persistent-over-N CTAs.  A = 128 query rows (hi, lo resident in shared memory), B = 128-row base
-//                tiles streamed by 2-D TMA (SWIZZLE_128B) through an mbarrier ring; one elected thread issues
-//                tcgen05.mma.kind::tf32 three times per k-step (hi*hi + hi*lo + lo*hi = "3xTF32", ~2^-21 relative)
-//                into a double-buffered 128x128 fp32 accumulator in TMEM; four epilogue warps read the accumulator
-//                with tcgen05.ld (one query row per thread), add ||b||^2 and keep, per row, the K best approximate
-//                scores seen so far; every base row whose score is within `margin` of the current K-th best is
-//                appended to the query's candidate list.  The margin bounds the approximation error of the score
-//                (see DESIGN.md), so the true top-K (in the reference's own fp32 arithmetic) is always a candidate.
+//                13 low mantissa bits cleared) and the row norms.  The base operand is written tile-major and
+//                pre-swizzled: one contiguous 32 KB record [hi | lo] per 128-row tile and 32-column k-block whose
+//                bytes are the SWIZZLE_128B shared-memory image the UMMA descriptor expects.
+//   2. gemm    : warp-specialised CTAs (one per SM), grid = query tiles x base splits.  The 128 query rows (hi, lo)
+//                are written ONCE into tensor memory (tcgen05.st) and stay there as the A operand; the B records are
+//                streamed by one linear cp.async.bulk per stage through a 6-deep mbarrier ring; one elected thread
+//                issues tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory) three times per k-step
+//                (hi*hi + hi*lo + lo*hi = "3xTF32", ~2^-21 relative) into a double-buffered 128x128 fp32
+//                accumulator in TMEM; eight epilogue warps (two per TMEM lane quarter, one column half each; one
+//                query row per thread) read the accumulator with tcgen05.ld, add ||b||^2 and flag, branch-free, the
+//                4-column groups holding a score within `margin` of the row's current K-th best; the rare flagged
+//                groups are re-read and every such base row is appended to the query's candidate list while a
+//                per-row sorted list of the K best approximate scores keeps the bound tight.  The bound is shared
+//                between the base splits of a query (global atomicMin) and tightened by a merger warp to the K-th
+//                smallest of the union of all published lists.  The margin bounds the approximation error of the
+//                score, so the true top-K (in the reference's own fp32 arithmetic) is always a
+//                candidate.
 //   3. rerank  : one warp per query recomputes its few hundred candidates with the reference's exact fp32
 //                summation order (same code as the traversal kernels) and selects the K smallest (distance, index)
 //                pairs -- identical ids and distances to src/ggnn/query/bf_query_layer.cu:39-65.
