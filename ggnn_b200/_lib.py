@@ -54,7 +54,7 @@ EXPORTS = [
     "ggnn_b200_graph_blob_offsets", "ggnn_b200_build_scratch_bytes", "ggnn_b200_query_shape_init",
     "ggnn_b200_query", "ggnn_b200_bf_query", "ggnn_b200_bf_query_workspace_bytes", "ggnn_b200_top", "ggnn_b200_nn1_stats", "ggnn_b200_select",
     "ggnn_b200_merge", "ggnn_b200_sym", "ggnn_b200_sym_buffer_merge", "ggnn_b200_build_graph",
-    "ggnn_b200_merge_topk",
+    "ggnn_b200_merge_topk", "ggnn_b200_widen_u8",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def lib():
         l.ggnn_b200_sym_buffer_merge.argtypes = [cfgp, u32, vp, vp, vp, vp]
         l.ggnn_b200_build_graph.argtypes = [cfgp, vp, i32, f32, u32, vp, vp, vp, sz, vp]
         l.ggnn_b200_merge_topk.argtypes = [vp, vp, u32, sz, sz, u32, u32, u32, C.c_int64, vp, vp, vp]
+        l.ggnn_b200_widen_u8.argtypes = [vp, vp, sz, vp]
         _lib = l
     return _lib
 

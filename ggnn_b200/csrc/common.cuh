@@ -271,6 +271,21 @@ struct WarpLists {
       dist[j] = G200_INF;
     }
   }
+  // common interface with SmemLists (the lists live in registers: no backing store needed)
+  __device__ __forceinline__ void init(uint32_t best, void*, uint32_t) { init(best); }
+
+  // simple_knn_cache.cuh:335-352 write_best: slots [0, K) -> ids (+ id_off) and distances
+  __device__ __forceinline__ void write_results(int* __restrict__ ids, float* __restrict__ dists, uint32_t K, int id_off) const
+  {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const uint32_t k = 32u * j + lane_id();
+      if (k < K) {
+        ids[k] = key[j] + id_off;
+        if (dists) dists[k] = dist[j];
+      }
+    }
+  }
 
   __device__ __forceinline__ float dist_at(uint32_t p) const
   {
@@ -371,6 +386,119 @@ struct WarpLists {
       hit |= (v.x == k) | (v.y == k) | (v.z == k) | (v.w == k);
     }
     return hit;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The same lists in SHARED memory, for SORTED sizes that do not fit the register file (KQuery up to 6000,
+// src/ggnn/query/query_kernels.cu:63-69).  Same slot-for-slot semantics as WarpLists (and therefore as
+// SimpleKNNCache::push/pop), processed 32 slots at a time with the previous chunk's boundary values carried
+// in registers, so every slot is read (old value) before it is overwritten.
+// ------------------------------------------------------------------------------------------------
+struct SmemLists {
+  int* key;        // [SORTED] shared, 16-byte aligned
+  float* dist;     // [SORTED] shared
+  uint32_t head;   // physical prioQ head (uniform)
+  uint32_t BEST;   // uniform
+  uint32_t SORTED; // multiple of 32
+
+  __device__ __forceinline__ void init(uint32_t best, void* smem, uint32_t sorted)
+  {
+    key = reinterpret_cast<int*>(smem);
+    dist = reinterpret_cast<float*>(key + sorted);
+    BEST = best;
+    head = best;
+    SORTED = sorted;
+    __syncwarp();
+    for (uint32_t p = lane_id(); p < sorted; p += 32) {
+      key[p] = EMPTY_KEY;
+      dist[p] = G200_INF;
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ float dist_at(uint32_t p) const { return dist[p]; }
+  __device__ __forceinline__ int key_at(uint32_t p) const { return key[p]; }
+
+  __device__ __forceinline__ void push(int k, float d)
+  {
+    const int lane = lane_id();
+    bool dup = false;
+    for (uint32_t p = lane; p < SORTED; p += 32) dup |= (key[p] == k);
+    if (__any_sync(FULL, dup)) return;  // :132-146
+
+    // asd[SORTED-1] is what slot BEST compares against (idx_prev = SORTED-1, :177)
+    const float od_l1 = dist[SORTED - 1], od_l2 = dist[SORTED - 2];
+    const int ok_l2 = key[SORTED - 2];
+    const bool recv_last = (SORTED - 1 != BEST) && (SORTED - 1 != head) && (od_l2 >= d) && (ok_l2 != EMPTY_KEY);
+    const float last_asd = recv_last ? od_l2 : od_l1;
+    __syncwarp();
+
+    int carry_k = EMPTY_KEY;
+    float carry_d = 0.f, carry_asd = 0.f;
+    for (uint32_t b = 0; b < SORTED; b += 32) {
+      const uint32_t p = b + lane;
+      const int ok = key[p];
+      const float od = dist[p];
+      int pk = __shfl_up_sync(FULL, ok, 1);
+      float pd = __shfl_up_sync(FULL, od, 1);
+      if (lane == 0) {
+        pk = carry_k;
+        pd = carry_d;
+      }
+      const bool recv = (p >= 1) && (p != BEST) && (p != head) && (pd >= d) && (pk != EMPTY_KEY);
+      const float asd = recv ? pd : od;
+      const int nk = recv ? pk : ok;
+      float pa = __shfl_up_sync(FULL, asd, 1);
+      if (lane == 0) pa = carry_asd;
+      if (p == BEST) pa = last_asd;
+      const bool active = od >= d;
+      const bool has_prev = (p != 0) && (p != head);
+      const bool ins = active && (!has_prev || pa < d);  // :176-182
+      carry_k = __shfl_sync(FULL, ok, 31);
+      carry_d = __shfl_sync(FULL, od, 31);
+      carry_asd = __shfl_sync(FULL, asd, 31);
+      if (ins || recv) {  // every lane writes only its own slot
+        key[p] = ins ? k : nk;
+        dist[p] = ins ? d : asd;
+      }
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ int pop(float criteria)
+  {
+    const int k = key[head];
+    const float dd = dist[head];
+    if (k == EMPTY_KEY || dd >= criteria) return EMPTY_KEY;
+    __syncwarp();
+    if (lane_id() == 0) {
+      key[head] = EMPTY_KEY;
+      dist[head] = G200_INF;
+    }
+    __syncwarp();
+    head = (head + 1 >= SORTED) ? BEST : head + 1;
+    return k;
+  }
+
+  // the keys already live in shared memory: nothing to mirror
+  __device__ __forceinline__ void store_keys(int*) const {}
+  __device__ __forceinline__ bool in_sorted(const int*, int k) const
+  {
+    bool hit = false;
+    const int4* s4 = reinterpret_cast<const int4*>(key);
+    for (uint32_t i = 0; i < SORTED / 4; ++i) {
+      const int4 v = s4[i];
+      hit |= (v.x == k) | (v.y == k) | (v.z == k) | (v.w == k);
+    }
+    return hit;
+  }
+
+  __device__ __forceinline__ void write_results(int* __restrict__ ids, float* __restrict__ dists, uint32_t K, int id_off) const
+  {
+    for (uint32_t k = lane_id(); k < K; k += 32) {
+      ids[k] = key[k] + id_off;
+      if (dists) dists[k] = dist[k];
+    }
   }
 };
 

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
     const uint32_t s_offset = (seg_btm / powG) * a.S;
     for (uint32_t i = 0; i < a.S; i += 32) {
       const int ck = (i + lane < a.S) ? static_cast<int>(s_offset + i + lane) : EMPTY_KEY;
-      fetch<NS, FAST, D32, NW, false>(L, V, ws, qv, a.base, a.translation + a.STs_offsets[a.layer_top], ck, xi, st);
+      fetch<WarpLists<NS>, FAST, D32, NW, false>(L, V, ws, qv, a.base, a.translation + a.STs_offsets[a.layer_top], ck, xi, st);
     }
   }
 
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
     const int32_t* tr = layer ? a.translation + a.STs_offsets[layer] : nullptr;
     if (layer == a.layer_btm) {  // :103-104
       const int ck = lane == 0 ? static_cast<int>(n) : EMPTY_KEY;
-      fetch<NS, FAST, D32, NW, false>(L, V, ws, qv, a.base, tr, ck, xi, st);
+      fetch<WarpLists<NS>, FAST, D32, NW, false>(L, V, ws, qv, a.base, tr, ck, xi, st);
     }
     const int32_t* layer_graph = a.graph + static_cast<size_t>(a.Ns_offsets[layer]) * K;
     SpecRow spec{EMPTY_KEY, EMPTY_KEY};
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
         if (use_spec && spec.key == anchor) ck = spec.row;  // speculative load issued before the previous push loop
         else ck = (j + lane < K) ? __ldg(layer_graph + static_cast<size_t>(anchor) * K + j + lane) : EMPTY_KEY;
         spec.key = EMPTY_KEY;
-        fetch<NS, FAST, D32, NW, true>(L, V, ws, qv, a.base, tr, ck, xi, st, use_spec ? layer_graph : nullptr, K,
+        fetch<WarpLists<NS>, FAST, D32, NW, true>(L, V, ws, qv, a.base, tr, ck, xi, st, use_spec ? layer_graph : nullptr, K,
                                        use_spec ? &spec : nullptr);
       }
     }
@@ -932,7 +932,10 @@ using namespace g200;
 static int check_cfg(const ggnn_b200_graph_config* cfg)
 {
   if (!cfg) return set_error(GGNN_B200_ERR_INVALID, "null graph config");
-  if (cfg->KBuild > 111) return set_error(GGNN_B200_ERR_UNSUPPORTED, "KBuild > 111 not built yet");
+  // KF + 16 must stay below the sym cache (128 slots): the reference aborts on CHECK_LT(sorted_size, CACHE_SIZE)
+  // (include/ggnn/construction/sym_query_layer.cuh:46,58-59) for KBuild > 161
+  if (cfg->KBuild > 161)
+    return set_error(GGNN_B200_ERR_INVALID, "KBuild > 161: sym sorted_size >= CACHE_SIZE (the reference CHECK-aborts)");
   return 0;
 }
 
@@ -980,6 +983,8 @@ extern "C" int ggnn_b200_top(const ggnn_b200_graph_config* cfg, const float* d_b
     case 2: G200_TOP(2, false, 1, 1);
     case 3: G200_TOP(3, false, 1, 1);
     case 4: G200_TOP(4, false, 1, 1);
+    case 5: G200_TOP(5, false, 1, 1);
+    case 6: G200_TOP(6, false, 1, 1);
   }
 #undef G200_TOP
   return set_error(GGNN_B200_ERR_UNSUPPORTED, "no top kernel variant");
@@ -1081,6 +1086,8 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
       case 2: G200_MERGE(2, false, 1, 1); break;
       case 3: G200_MERGE(3, false, 1, 1); break;
       case 4: G200_MERGE(4, false, 1, 1); break;
+      case 5: G200_MERGE(5, false, 1, 1); break;
+      case 6: G200_MERGE(6, false, 1, 1); break;
       default: return set_error(GGNN_B200_ERR_UNSUPPORTED, "no merge kernel variant");
     }
   }

@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -61,3 +62,39 @@ uint32_t env_u32(const char* name, uint32_t dflt)
 
 extern "C" const char* ggnn_b200_last_error(void) { return g200::g_err; }
 extern "C" const char* ggnn_b200_version(void) { return "ggnn_b200 0.1 (sm_100a; cp.async.bulk staged traversal)"; }
+
+// uint8 -> fp32 widening (see ggnn_b200.h); 16 values per thread: one 16-byte load, four 16-byte stores
+namespace g200 {
+__global__ void __launch_bounds__(256) widen_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t count)
+{
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n16 = count / 16;
+  const bool aligned = (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  size_t done = 0;
+  if (aligned) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float4* o = reinterpret_cast<float4*>(dst) + 4 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = make_float4(static_cast<float>(w[j] & 0xffu), static_cast<float>((w[j] >> 8) & 0xffu),
+                           static_cast<float>((w[j] >> 16) & 0xffu), static_cast<float>(w[j] >> 24));
+    }
+    done = n16 * 16;
+  }
+  for (size_t i = done + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
+    dst[i] = static_cast<float>(src[i]);
+}
+}  // namespace g200
+
+extern "C" int ggnn_b200_widen_u8(const uint8_t* d_src, float* d_dst, size_t count, ggnn_b200_stream_t stream_)
+{
+  if (!count) return 0;
+  if (!d_src || !d_dst) return g200::set_error(GGNN_B200_ERR_INVALID, "null device pointer");
+  const g200::DeviceInfo& dev = g200::device_info();
+  const size_t want = (count / 16 + 255) / 256 + 1;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(dev.num_sms) * 8));
+  g200::widen_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(d_src, d_dst, count);
+  return g200::set_cuda_error(cudaGetLastError(), "widen_u8_kernel launch");
+}

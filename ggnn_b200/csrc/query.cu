@@ -25,9 +25,11 @@ struct QueryArgs {
   uint32_t hsize;      // visited hash slots (power of two)
   uint32_t ring_cap;   // 0 = ring mirror not needed
   uint32_t off_sq, off_sorted, off_hash, off_ring, off_bar;  // byte offsets in the per-warp block
+  uint32_t off_lists;  // SmemLists backing store (sorted_size > 256 only)
 };
 
-template <int NS, bool FAST, int NI>
+// LT = WarpLists<NS> (best list + prioQ in registers, sorted_size <= 256) or SmemLists (anything larger)
+template <class LT, bool FAST, int NI>
 __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -72,15 +74,15 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
   while (n < a.N_query) {
     QueryVec<FAST, NI, 1> qv;
     qv.load(dc, p.d_query + static_cast<size_t>(n) * p.D, ws.s_q);
-    WarpLists<NS> L;
-    L.init(p.KQuery);
+    LT L;
+    L.init(p.KQuery, wbase + a.off_lists, p.sorted_size);
     V.clear();
     Stats st{0, 0};
 
     // query_layer.cu:55 fetch_unfiltered(d_starting_points, nullptr, S)
     for (uint32_t i = 0; i < p.num_starting_points; i += 32) {
       const int ck = (i + lane < p.num_starting_points) ? p.d_starting_points[i + lane] : EMPTY_KEY;
-      fetch<NS, FAST, NI, 1, false>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st, a.prefetch ? p.d_graph : nullptr,
+      fetch<LT, FAST, NI, 1, false>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st, a.prefetch ? p.d_graph : nullptr,
                                     p.KBuild);
     }
 
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
         else
           ck = (i + lane < p.KBuild) ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane) : EMPTY_KEY;
         spec.key = EMPTY_KEY;
-        fetch<NS, FAST, NI, 1, true>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
+        fetch<LT, FAST, NI, 1, true>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
                                      p.KBuild, use_spec ? &spec : nullptr);
       }
     }
@@ -112,14 +114,8 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
     // :81-90 (+ simple_knn_cache.cuh:344-352)
     const size_t row = (static_cast<size_t>(n) * p.shards_per_gpu + p.on_gpu_shard_id) * p.KQuery;
     const int id_off = static_cast<int>(p.on_gpu_shard_id) * p.N_base;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const uint32_t k = 32u * j + lane;
-      if (k < p.KQuery) {
-        p.d_query_results[row + k] = L.key[j] + id_off;
-        if (p.d_query_results_dists) p.d_query_results_dists[row + k] = L.dist[j];
-      }
-    }
+    L.write_results(p.d_query_results + row, p.d_query_results_dists ? p.d_query_results_dists + row : nullptr, p.KQuery,
+                    id_off);
     if (p.d_stats && lane == 0) {
       p.d_stats[2 * static_cast<size_t>(n)] = st.pops;
       p.d_stats[2 * static_cast<size_t>(n) + 1] = st.dists;
@@ -135,10 +131,10 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
   }
 }
 
-template <int NS, bool FAST, int NI>
+template <class LT, bool FAST, int NI>
 static int launch(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream)
 {
-  auto kern = query_kernel<NS, FAST, NI>;
+  auto kern = query_kernel<LT, FAST, NI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(query_kernel)");
   kern<<<grid, a.warps_per_cta * 32, smem, stream>>>(a);
@@ -194,7 +190,8 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   if (p.KBuild == 0 || p.N_base <= 0) return set_error(GGNN_B200_ERR_INVALID, "bad KBuild / N_base");
   if (N_query == 0) return 0;
   const int NS = p.sorted_size / 32;
-  if (NS > 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "sorted_size > 128 (KQuery > 111) not built yet");
+  // register-resident lists up to 256 slots (KQuery <= 239); beyond that the lists live in shared memory
+  const bool smem_lists = NS > 8;
   if (p.d_work_counter) {
     cudaError_t e = cudaMemsetAsync(p.d_work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(work counter)");
@@ -210,7 +207,9 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   const uint32_t vcap = p.cache_size - p.sorted_size;
   a.ring_cap = (vcap < p.max_iterations) ? vcap : 0;
   a.hsize = std::max(64u, 2u * bit_ceil_u32(std::max(1u, p.max_iterations)));
-  const uint32_t fixed = (fast ? 0 : align_up(row_bytes, 16)) + p.sorted_size * 4 + a.hsize * 4 +
+  const uint32_t sorted_mirror = smem_lists ? 128u : p.sorted_size * 4;  // SmemLists only need 32 ints of scratch
+  const uint32_t lists_bytes = smem_lists ? p.sorted_size * 8 : 0;
+  const uint32_t fixed = (fast ? 0 : align_up(row_bytes, 16)) + sorted_mirror + lists_bytes + a.hsize * 4 +
                          align_up(a.ring_cap * 4, 16) + 32;
   a.warps_per_cta = std::min(4u, std::max(1u, env_u32("GGNN_B200_QUERY_WARPS", 4)));
   const uint32_t target_warps_per_sm = env_u32("GGNN_B200_QUERY_WARPS_PER_SM", 16);
@@ -227,7 +226,9 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   a.off_sq = off;
   off += fast ? 0 : align_up(row_bytes, 16);
   a.off_sorted = off;
-  off += p.sorted_size * 4;
+  off += sorted_mirror;
+  a.off_lists = off;
+  off += lists_bytes;
   a.off_hash = off;
   off += a.hsize * 4;
   a.off_ring = off;
@@ -249,7 +250,8 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
     grid = std::min(ctas_needed, per_sm * dev.num_sms);
   }
 
-#define G200_LAUNCH(NS_, FAST_, NI_) return launch<NS_, FAST_, NI_>(a, grid, smem, stream)
+#define G200_LAUNCH(NS_, FAST_, NI_) return launch<WarpLists<NS_>, FAST_, NI_>(a, grid, smem, stream)
+  if (smem_lists) return launch<SmemLists, false, 1>(a, grid, smem, stream);
   if (fast) {
     switch (NS * 10 + NI) {
       case 11: G200_LAUNCH(1, true, 1);
@@ -268,6 +270,10 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
     case 2: G200_LAUNCH(2, false, 1);
     case 3: G200_LAUNCH(3, false, 1);
     case 4: G200_LAUNCH(4, false, 1);
+    case 5: G200_LAUNCH(5, false, 1);
+    case 6: G200_LAUNCH(6, false, 1);
+    case 7: G200_LAUNCH(7, false, 1);
+    case 8: G200_LAUNCH(8, false, 1);
   }
 #undef G200_LAUNCH
   return set_error(GGNN_B200_ERR_UNSUPPORTED, "no kernel variant");

@@ -12,7 +12,7 @@ namespace g200 {
 struct WarpSmem {
   float* stage;      // [stage_rows * D], 16-byte aligned
   float* s_q;        // [D] query copy (generic distance path / sym half-way point), may be null
-  int* s_sorted;     // [32*NS] mirror of the sorted keys for the filter
+  int* s_sorted;     // [32*NS] mirror of the sorted keys for the filter (register lists); >= 32 ints of scratch
   uint64_t* bar;     // mbarriers for the bulk copies: bar[0..3], one per 8-row stage group
   uint32_t parity;   // phase bit of bar[i] in bit i
   uint32_t stage_rows;  // multiple of 8
@@ -238,8 +238,8 @@ struct SpecRow {
   int row;  // lane l: adjacency entry l of `key`
 };
 
-template <int NS, bool FAST, int D32, int NW, bool FILTER>
-__device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, WarpSmem& ws,
+template <class LT, bool FAST, int D32, int NW, bool FILTER>
+__device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
                                       const QueryVec<FAST, D32, NW>& qv, const float* __restrict__ base,
                                       const int* __restrict__ translation, int ck, float xi, Stats& st,
                                       const int* __restrict__ pf_graph = nullptr, uint32_t pf_stride = 0,
@@ -251,7 +251,7 @@ __device__ __forceinline__ void fetch(WarpLists<NS>& L, const VisitedSet& V, War
     __syncwarp();
     L.store_keys(ws.s_sorted);
     __syncwarp();
-    if (valid) valid = !WarpLists<NS>::in_sorted(ws.s_sorted, ck) && !V.contains(ck);
+    if (valid) valid = !L.in_sorted(ws.s_sorted, ck) && !V.contains(ck);
   }
   const unsigned mask = __ballot_sync(FULL, valid);
   const int cnt = __popc(mask);

@@ -1,25 +1,31 @@
-// ggnn.hpp -- header-only C++20 host API over the C ABI (ggnn_b200.h), mirroring the reference's public class
-// ggnn::GGNN<KeyT, ValueT> (include/ggnn/base/ggnn.cuh:41-182) and its value types Dataset<T> / Results
-// (include/ggnn/base/dataset.cuh:93-166), so that programs written against the reference -- e.g.
-// examples/cpp-and-cuda/ggnn_main.cpp -- compile against this header and link libggnn_b200.so + libcudart.
+// ggnn.hpp -- header-only C++20 host API over the C ABI (ggnn_b200.h), mirroring the reference's public
+// surface: ggnn::GGNN<KeyT, ValueT> (include/ggnn/base/ggnn.cuh:41-182), the value types GenericDataset /
+// Dataset<T> / Results (include/ggnn/base/dataset.cuh:38-166, data.cuh:26-149) and Evaluator / Evaluation
+// (include/ggnn/base/eval.h:31-65), so that programs written against the reference -- its own
+// examples/cpp-and-cuda/{ggnn_main.cpp, ggnn_main_gpu_data.cu, ggnn_main_multi_gpu.cpp, ggnn_benchmark.cpp} --
+// compile unchanged against this header tree and link libggnn_b200.so + libcudart.
 //
-// Same method names, argument meaning, defaults and error behaviour (std::runtime_error / std::out_of_range for
-// API misuse).  All computation happens in the sm_100a kernels behind the C ABI; there is no CPU fallback.
-// Differences (documented in DESIGN.md): datasets are fp32 / int32 only (uint8 base vectors are a "next" row),
-// shards stay resident in HBM (no swap to host / disk), multi-GPU results are merged on GPU 0 by a kernel
-// instead of the reference's CPU heap merge.
+// Same names, argument meaning, defaults and error behaviour (std::runtime_error / std::out_of_range for API
+// misuse).  All computation happens in the sm_100a kernels behind the C ABI; there is no CPU fallback.
+// Differences: uint8 vectors are widened to fp32 once on the device (bit-identical results, see
+// ggnn_b200_widen_u8), shards stay resident in HBM (no swap to host / disk), multi-GPU results are merged on
+// the first GPU by a kernel instead of the reference's CPU heap merge.
 #pragma once
 
 #include <ggnn_b200.h>
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <fstream>
 #include <limits>
 #include <memory>
+#include <ostream>
 #include <span>
 #include <stdexcept>
 #include <string>
@@ -30,9 +36,50 @@ namespace ggnn {
 
 enum class DistanceMeasure : int { Euclidean = 0, Cosine = 1 };  // include/ggnn/base/def.h:27-30
 
-enum class DataLocation : uint16_t { UNKNOWN, GPU, MANAGED, CPU_PINNED, CPU_MALLOC, FOREIGN_GPU, FOREIGN_CPU };  // data.cuh:36-44
+// include/ggnn/base/data.cuh:26-44
+enum class DataType : uint16_t { UNKNOWN, BYTE, UINT8, INT32, UINT32, FLOAT };
+enum class DataLocation : uint16_t { UNKNOWN, GPU, MANAGED, CPU_PINNED, CPU_MALLOC, FOREIGN_GPU, FOREIGN_CPU };
+
+inline std::ostream& operator<<(std::ostream& os, DataType t)
+{
+  static constexpr const char* names[] = {"unknown", "byte", "uint8", "int32", "uint32", "float"};
+  return os << names[static_cast<size_t>(t)];
+}
+inline std::ostream& operator<<(std::ostream& os, DataLocation l)
+{
+  static constexpr const char* names[] = {"unknown", "GPU", "managed", "CPU (pinned)", "CPU", "GPU (foreign)", "CPU (foreign)"};
+  return os << names[static_cast<size_t>(l)];
+}
 
 namespace detail {
+template <typename T> struct TypeTag;
+template <> struct TypeTag<std::byte> { static constexpr DataType value = DataType::BYTE; };
+template <> struct TypeTag<uint8_t> { static constexpr DataType value = DataType::UINT8; };
+template <> struct TypeTag<int32_t> { static constexpr DataType value = DataType::INT32; };
+template <> struct TypeTag<uint32_t> { static constexpr DataType value = DataType::UINT32; };
+template <> struct TypeTag<float> { static constexpr DataType value = DataType::FLOAT; };
+
+inline size_t dataSize(DataType t)
+{
+  switch (t) {
+    case DataType::BYTE:
+    case DataType::UINT8: return 1;
+    case DataType::INT32:
+    case DataType::UINT32:
+    case DataType::FLOAT: return 4;
+    default: return 0;
+  }
+}
+inline DataLocation disown(DataLocation l)
+{
+  switch (l) {
+    case DataLocation::GPU:
+    case DataLocation::MANAGED: return DataLocation::FOREIGN_GPU;
+    case DataLocation::CPU_PINNED:
+    case DataLocation::CPU_MALLOC: return DataLocation::FOREIGN_CPU;
+    default: return l;
+  }
+}
 inline void cuda_check(cudaError_t e, const char* what)
 {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
@@ -52,37 +99,42 @@ struct DeviceGuard {
     cuda_check(cudaSetDevice(dev), "cudaSetDevice");
   }
   ~DeviceGuard() { cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 }  // namespace detail
 
-/// 2-D row-major buffer, owning or referencing, on host or device (dataset.cuh:93-160)
 template <typename T>
-struct Dataset {
+constexpr DataType DataType_v = detail::TypeTag<std::remove_const_t<T>>::value;
+
+template <typename T>
+struct Dataset;
+
+/// type-erased 2-D row-major buffer, owning or referencing, on host or device (dataset.cuh:38-91)
+struct GenericDataset {
   uint64_t N{0};
   uint32_t D{0};
+  DataType type{DataType::UNKNOWN};
   DataLocation location{DataLocation::UNKNOWN};
   int32_t gpu_id{-1};
 
-  Dataset() = default;
-  Dataset(const Dataset&) = delete;
-  Dataset& operator=(const Dataset&) = delete;
-  Dataset(Dataset&& o) noexcept { *this = std::move(o); }
-  Dataset& operator=(Dataset&& o) noexcept
+  GenericDataset() = default;
+  GenericDataset(const GenericDataset&) = delete;
+  GenericDataset& operator=(const GenericDataset&) = delete;
+  GenericDataset(GenericDataset&& o) noexcept { take(o); }
+  GenericDataset& operator=(GenericDataset&& o) noexcept
   {
     if (this != &o) {
       release();
-      N = o.N; D = o.D; location = o.location; gpu_id = o.gpu_id; mem = o.mem;
-      o.mem = nullptr; o.N = 0; o.location = DataLocation::UNKNOWN;
+      take(o);
     }
     return *this;
   }
-  ~Dataset() { release(); }
+  virtual ~GenericDataset() { release(); }
 
-  T* data() { return mem; }
-  const T* data() const { return mem; }
   size_t numel() const { return static_cast<size_t>(N) * D; }
-  size_t size() const { return numel(); }
-  size_t size_bytes() const { return numel() * sizeof(T); }
+  size_t element_size() const { return detail::dataSize(type); }
+  size_t required_size_bytes() const { return element_size() * numel(); }
   bool isCPUAccessible() const
   {
     return location == DataLocation::CPU_MALLOC || location == DataLocation::CPU_PINNED ||
@@ -92,104 +144,99 @@ struct Dataset {
   {
     return location == DataLocation::GPU || location == DataLocation::FOREIGN_GPU || location == DataLocation::MANAGED;
   }
-  T& operator[](size_t i) { return mem[i]; }
-  const T& operator[](size_t i) const { return mem[i]; }
-  T& at(size_t i)
-  {
-    if (i >= numel()) throw std::out_of_range("Index " + std::to_string(i) + " is out of bounds (size " + std::to_string(numel()) + ").");
-    return mem[i];
-  }
-  const T& at(size_t i) const { return const_cast<Dataset*>(this)->at(i); }
-  operator T*() { return mem; }
-  operator const T*() const { return mem; }
+  /// the memory will not be freed by this object any more
+  void releaseOwnership() { location = detail::disown(location); }
 
-  static Dataset empty(uint64_t N, uint32_t D, bool pin_memory = false)
+  /// non-owning alias of the whole buffer / of rows [from, from + num)
+  GenericDataset reference() const { return referenceRange(0, N); }
+  GenericDataset referenceRange(uint64_t from, uint64_t num) const
   {
-    Dataset d;
-    d.N = N; d.D = D;
-    if (pin_memory) {
-      detail::cuda_check(cudaMallocHost(reinterpret_cast<void**>(&d.mem), d.size_bytes()), "cudaMallocHost");
-      d.location = DataLocation::CPU_PINNED;
+    if (from + num > N) throw std::out_of_range("referenceRange: rows out of bounds");
+    GenericDataset r;
+    r.N = num;
+    r.D = D;
+    r.type = type;
+    r.location = detail::disown(location);
+    r.gpu_id = gpu_id;
+    r.mem = static_cast<char*>(mem) + from * D * element_size();
+    return r;
+  }
+
+  template <typename T>
+  std::span<T> reinterpret() { return {reinterpret_cast<T*>(mem), numel()}; }
+  template <typename T>
+  std::span<const T> reinterpret() const { return {reinterpret_cast<const T*>(mem), numel()}; }
+  template <typename T>
+  std::span<T> access()
+  {
+    check_type<T>();
+    return reinterpret<T>();
+  }
+  template <typename T>
+  std::span<const T> access() const
+  {
+    check_type<T>();
+    return reinterpret<T>();
+  }
+  explicit operator void*() { return mem; }
+  explicit operator const void*() const { return mem; }
+
+  /// .fvecs / .bvecs / .ivecs by file extension (src/ggnn/base/dataset.cu:118-131)
+  static GenericDataset load(const std::filesystem::path& file, uint32_t from = 0,
+                             uint32_t num = std::numeric_limits<uint32_t>::max(), bool pin_memory = false);
+
+  /// uninitialised owning buffer
+  static GenericDataset allocate(uint64_t N, uint32_t D, DataType type, DataLocation where, int32_t gpu_id = -1)
+  {
+    GenericDataset d;
+    d.N = N;
+    d.D = D;
+    d.type = type;
+    d.gpu_id = gpu_id;
+    const size_t bytes = std::max<size_t>(16, d.required_size_bytes());
+    switch (where) {
+      case DataLocation::GPU: {
+        detail::DeviceGuard g(gpu_id);
+        detail::cuda_check(cudaMalloc(&d.mem, bytes), "cudaMalloc");
+        break;
+      }
+      case DataLocation::CPU_PINNED: detail::cuda_check(cudaMallocHost(&d.mem, bytes), "cudaMallocHost"); break;
+      case DataLocation::CPU_MALLOC:
+        d.mem = std::malloc(bytes);
+        if (!d.mem) throw std::bad_alloc();
+        break;
+      default: throw std::invalid_argument("allocate: unsupported location");
     }
-    else {
-      d.mem = static_cast<T*>(std::malloc(std::max<size_t>(1, d.size_bytes())));
-      if (!d.mem) throw std::bad_alloc();
-      d.location = DataLocation::CPU_MALLOC;
-    }
+    d.location = where;
     return d;
   }
-  static Dataset emptyOnGPU(uint64_t N, uint32_t D, int32_t gpu_id)
+  /// non-owning view of foreign memory
+  static GenericDataset foreign(void* data, uint64_t N, uint32_t D, DataType type, DataLocation where, int32_t gpu_id = -1)
   {
-    Dataset d;
-    d.N = N; d.D = D; d.gpu_id = gpu_id;
-    detail::DeviceGuard g(gpu_id);
-    detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&d.mem), std::max<size_t>(16, d.size_bytes())), "cudaMalloc");
-    d.location = DataLocation::GPU;
-    return d;
-  }
-  static Dataset copy(const std::span<const T>& data, uint32_t D, bool pin_memory = false)
-  {
-    if (D == 0 || data.size() % D) throw std::invalid_argument("data size is not a multiple of D");
-    Dataset d = empty(data.size() / D, D, pin_memory);
-    std::memcpy(d.mem, data.data(), d.size_bytes());
-    return d;
-  }
-  static Dataset referenceCPUData(T* data, uint64_t N, uint32_t D)
-  {
-    Dataset d;
-    d.N = N; d.D = D; d.mem = data; d.location = DataLocation::FOREIGN_CPU;
-    return d;
-  }
-  static Dataset referenceGPUData(T* data, uint64_t N, uint32_t D, int32_t gpu_id)
-  {
-    Dataset d;
-    d.N = N; d.D = D; d.mem = data; d.gpu_id = gpu_id; d.location = DataLocation::FOREIGN_GPU;
-    return d;
-  }
-  /// fvecs / ivecs: [int32 D][D values] per row (src/ggnn/base/dataset.cu:118-233)
-  static Dataset load(const std::filesystem::path& file, uint32_t from = 0,
-                      uint32_t num = std::numeric_limits<uint32_t>::max(), bool pin_memory = false)
-  {
-    std::ifstream f(file, std::ios::binary);
-    if (!f) throw std::runtime_error("cannot open " + file.string());
-    int32_t dim = 0;
-    f.read(reinterpret_cast<char*>(&dim), 4);
-    const size_t rec = 4 + static_cast<size_t>(dim) * sizeof(T);
-    const size_t total = std::filesystem::file_size(file) / rec;
-    const size_t lo = std::min<size_t>(from, total), hi = std::min<size_t>(total, static_cast<size_t>(from) + num);
-    Dataset d = empty(hi - lo, static_cast<uint32_t>(dim), pin_memory);
-    for (size_t r = lo; r < hi; ++r) {
-      f.seekg(static_cast<std::streamoff>(r * rec + 4));
-      f.read(reinterpret_cast<char*>(d.mem + (r - lo) * dim), static_cast<std::streamsize>(dim * sizeof(T)));
-    }
-    return d;
-  }
-  void store(const std::filesystem::path& file) const
-  {
-    if (!isCPUAccessible()) throw std::runtime_error("store() needs CPU-accessible data");
-    std::ofstream f(file, std::ios::binary);
-    const int32_t dim = static_cast<int32_t>(D);
-    for (uint64_t r = 0; r < N; ++r) {
-      f.write(reinterpret_cast<const char*>(&dim), 4);
-      f.write(reinterpret_cast<const char*>(mem + r * D), static_cast<std::streamsize>(D * sizeof(T)));
-    }
-  }
-  void copyTo(Dataset& other, cudaStream_t stream = nullptr) const
-  {
-    if (other.numel() != numel()) throw std::invalid_argument("copyTo: size mismatch");
-    detail::cuda_check(cudaMemcpyAsync(other.mem, mem, size_bytes(), cudaMemcpyDefault, stream), "cudaMemcpyAsync");
-    if (!isGPUAccessible() || !other.isGPUAccessible()) detail::cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
-  }
-  Dataset clone(cudaStream_t stream = nullptr) const
-  {
-    Dataset d = isGPUAccessible() && !isCPUAccessible() ? emptyOnGPU(N, D, gpu_id) : empty(N, D, location == DataLocation::CPU_PINNED);
-    copyTo(d, stream);
+    GenericDataset d;
+    d.N = N;
+    d.D = D;
+    d.type = type;
+    d.location = where;
+    d.gpu_id = gpu_id;
+    d.mem = data;
     return d;
   }
 
- private:
-  T* mem{nullptr};
-  void release()
+ protected:
+  void* mem{nullptr};
+
+  template <typename T>
+  void check_type() const
+  {
+    if (mem && DataType_v<T> != type) throw std::invalid_argument("dataset holds a different element type");
+  }
+  void take(GenericDataset& o) noexcept
+  {
+    N = o.N; D = o.D; type = o.type; location = o.location; gpu_id = o.gpu_id; mem = o.mem;
+    o.mem = nullptr; o.N = 0; o.location = DataLocation::UNKNOWN;
+  }
+  void release() noexcept
   {
     if (!mem) return;
     switch (location) {
@@ -197,18 +244,289 @@ struct Dataset {
       case DataLocation::MANAGED: cudaFree(mem); break;
       case DataLocation::CPU_PINNED: cudaFreeHost(mem); break;
       case DataLocation::CPU_MALLOC: std::free(mem); break;
-      default: break;  // FOREIGN_*: never freed (data.cu:147-149)
+      default: break;  // FOREIGN_*: never freed (src/ggnn/base/data.cu:147-149)
     }
     mem = nullptr;
   }
 };
 
-using GenericDataset = Dataset<float>;  // only float base / query vectors are built here
+/// typed view of a GenericDataset with the std::span-like access of the reference's Dataset<T> (dataset.cuh:93-160)
+template <typename T>
+struct Dataset : public GenericDataset {
+  using element_type = T;
+  using value_type = std::remove_cv_t<T>;
+  using iterator = T*;
+
+  Dataset() { type = DataType_v<T>; }
+  Dataset(GenericDataset&& g) : GenericDataset{std::move(g)}
+  {
+    if (!mem) type = DataType_v<T>;
+    check_type<T>();
+  }
+  Dataset(Dataset&&) noexcept = default;
+  Dataset& operator=(Dataset&&) noexcept = default;
+
+  T* data() const { return static_cast<T*>(mem); }
+  size_t size() const { return numel(); }
+  size_t size_bytes() const { return numel() * sizeof(T); }
+  bool empty() const { return numel() == 0; }
+  T* begin() const { return data(); }
+  T* end() const { return data() + numel(); }
+  T& operator[](size_t i) const { return data()[i]; }
+  T& at(size_t i) const
+  {
+    if (i >= numel()) throw std::out_of_range("Index " + std::to_string(i) + " is out of bounds (size " + std::to_string(numel()) + ").");
+    return data()[i];
+  }
+  T& front() const { return data()[0]; }
+  T& back() const { return data()[numel() - 1]; }
+  std::span<T> subspan(size_t offset, size_t count = std::dynamic_extent) const { return std::span<T>{data(), numel()}.subspan(offset, count); }
+  operator std::span<T>() const { return {data(), numel()}; }
+  operator T*() { return data(); }
+  operator const T*() const { return data(); }
+
+  static Dataset empty(uint64_t N, uint32_t D, bool pin_memory = false)
+  {
+    return Dataset{allocate(N, D, DataType_v<T>, pin_memory ? DataLocation::CPU_PINNED : DataLocation::CPU_MALLOC)};
+  }
+  static Dataset emptyOnGPU(uint64_t N, uint32_t D, int32_t gpu_id)
+  {
+    return Dataset{allocate(N, D, DataType_v<T>, DataLocation::GPU, gpu_id)};
+  }
+  static Dataset copy(const std::span<const T>& data, uint32_t D, bool pin_memory = false)
+  {
+    if (D == 0 || data.size() % D) throw std::invalid_argument("data size is not a multiple of D");
+    Dataset d = empty(data.size() / D, D, pin_memory);
+    std::memcpy(d.data(), data.data(), d.size_bytes());
+    return d;
+  }
+  static Dataset referenceCPUData(T* data, uint64_t N, uint32_t D)
+  {
+    return Dataset{foreign(const_cast<value_type*>(data), N, D, DataType_v<T>, DataLocation::FOREIGN_CPU)};
+  }
+  static Dataset referenceGPUData(T* data, uint64_t N, uint32_t D, int32_t gpu_id)
+  {
+    return Dataset{foreign(const_cast<value_type*>(data), N, D, DataType_v<T>, DataLocation::FOREIGN_GPU, gpu_id)};
+  }
+
+  /// [u]vecs files: per row a 4-byte dimension followed by D values (src/ggnn/base/dataset.cu:133-202); asking for
+  /// more rows than the file holds is an error there (CHECK_EQ) and here
+  static Dataset load(const std::filesystem::path& file, uint32_t from = 0,
+                      uint32_t num = std::numeric_limits<uint32_t>::max(), bool pin_memory = false)
+  {
+    std::ifstream f(file, std::ios::binary);
+    if (!f) throw std::runtime_error("Unable to open file " + file.string() + " for reading.");
+    uint32_t dim = 0;
+    f.read(reinterpret_cast<char*>(&dim), 4);
+    if (!f || dim == 0) throw std::runtime_error("Failed to read vectors from " + file.string() + ".");
+    const size_t rec = 4 + static_cast<size_t>(dim) * sizeof(T);
+    const size_t total = static_cast<size_t>(std::filesystem::file_size(file)) / rec;
+    if (from > total) throw std::out_of_range("Dataset contains fewer vectors than requested.");
+    size_t n = total - from;
+    if (num != std::numeric_limits<uint32_t>::max()) {
+      if (n < num) throw std::out_of_range("Dataset contains fewer vectors than requested.");
+      n = num;
+    }
+    Dataset d = empty(n, dim, pin_memory);
+    constexpr size_t rows_per_block = 4096;
+    std::vector<char> buf(rows_per_block * rec);
+    f.seekg(static_cast<std::streamoff>(from * rec));
+    for (size_t r0 = 0; r0 < n; r0 += rows_per_block) {
+      const size_t nr = std::min(rows_per_block, n - r0);
+      f.read(buf.data(), static_cast<std::streamsize>(nr * rec));
+      if (!f) throw std::runtime_error("Failed to read vectors from " + file.string() + ".");
+      for (size_t r = 0; r < nr; ++r) std::memcpy(d.data() + (r0 + r) * dim, buf.data() + r * rec + 4, dim * sizeof(T));
+    }
+    return d;
+  }
+  void store(const std::filesystem::path& file) const
+  {
+    if (!isCPUAccessible()) throw std::runtime_error("store() needs CPU-accessible data");
+    std::ofstream f(file, std::ios::binary | std::ios::trunc);
+    if (!f) throw std::runtime_error("Unable to open file " + file.string() + " for writing.");
+    const uint32_t dim = D;
+    for (uint64_t r = 0; r < N; ++r) {
+      f.write(reinterpret_cast<const char*>(&dim), 4);
+      f.write(reinterpret_cast<const char*>(data() + r * D), static_cast<std::streamsize>(D * sizeof(T)));
+    }
+  }
+  void copyTo(Dataset& other, cudaStream_t stream = nullptr) const { copyRangeTo(0, N, other, stream); }
+  /// rows [from, from + num) -> the first num rows of `other`
+  void copyRangeTo(uint64_t from, uint64_t num, Dataset& other, cudaStream_t stream = nullptr) const
+  {
+    if (from + num > N || num > other.N || other.D != D) throw std::invalid_argument("copyRangeTo: shape mismatch");
+    if (isCPUAccessible() && other.isCPUAccessible()) {  // host to host: no CUDA call needed
+      std::memcpy(other.data(), data() + from * D, num * D * sizeof(T));
+      return;
+    }
+    detail::cuda_check(cudaMemcpyAsync(other.data(), data() + from * D, num * D * sizeof(T), cudaMemcpyDefault, stream), "cudaMemcpyAsync");
+    if (!isGPUAccessible() || !other.isGPUAccessible()) detail::cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  }
+  Dataset clone(cudaStream_t stream = nullptr) const
+  {
+    Dataset d = isGPUAccessible() && !isCPUAccessible() ? emptyOnGPU(N, D, gpu_id) : empty(N, D, location == DataLocation::CPU_PINNED);
+    if (numel()) copyTo(d, stream);
+    return d;
+  }
+  /// the data itself if it already lives on `gpu`, else a device copy (dataset.cu:325-334)
+  Dataset referenceOnGPU(int gpu, cudaStream_t stream = nullptr) const
+  {
+    if (isGPUAccessible() && (gpu_id == gpu || location == DataLocation::MANAGED)) return Dataset{reference()};
+    Dataset d = emptyOnGPU(N, D, gpu);
+    detail::DeviceGuard g(gpu);
+    detail::cuda_check(cudaMemcpyAsync(d.data(), data(), size_bytes(), cudaMemcpyDefault, stream), "cudaMemcpyAsync");
+    return d;
+  }
+};
+
+inline GenericDataset GenericDataset::load(const std::filesystem::path& file, uint32_t from, uint32_t num, bool pin_memory)
+{
+  const std::string name = file.string();
+  if (name.ends_with(".fvecs")) return GenericDataset{Dataset<float>::load(file, from, num, pin_memory)};
+  if (name.ends_with(".bvecs")) return GenericDataset{Dataset<uint8_t>::load(file, from, num, pin_memory)};
+  if (name.ends_with(".ivecs")) return GenericDataset{Dataset<int32_t>::load(file, from, num, pin_memory)};
+  throw std::runtime_error("Could not guess file type from " + name + ". fvecs, bvecs, or ivecs file required.");
+}
 
 template <typename KeyT, typename ValueT>
 struct Results {
   Dataset<KeyT> ids{};
   Dataset<ValueT> dists{};
+};
+
+// ------------------------------------------------------------------------------------------------
+// Evaluation (include/ggnn/base/eval.h:31-65, src/ggnn/base/eval.cpp:37-242)
+// ------------------------------------------------------------------------------------------------
+struct GTDuplicates {
+  std::vector<uint32_t> top1DuplicateEnd{};
+  std::vector<uint32_t> topKDuplicateEnd{};
+};
+
+struct Evaluation {
+  uint32_t KQuery{};
+  float c1{0}, c1_dup{0}, cKQuery{0}, cKQuery_dup{0}, rKQuery{0}, rKQuery_dup{0};
+};
+
+inline std::ostream& operator<<(std::ostream& os, const Evaluation& e)
+{
+  auto dup = [&os](float v, bool newline) {
+    if (!std::isnan(v)) os << " +duplicates: " << v;
+    else os << " (duplicates unknown)";
+    if (newline) os << '\n';
+  };
+  os << "c@1 (=r@1): " << e.c1;
+  dup(e.c1_dup, true);
+  os << "c@" << e.KQuery << ": " << e.cKQuery;
+  dup(e.cKQuery_dup, true);
+  os << "r@" << e.KQuery << ": " << e.rKQuery;
+  dup(e.rKQuery_dup, false);
+  return os;
+}
+
+template <typename KeyT, typename ValueT>
+struct Evaluator {
+  uint32_t KQuery{0};
+  DistanceMeasure measure{};
+  Dataset<KeyT> gt;
+  GTDuplicates gt_duplicates{};
+
+  Evaluator() = default;
+
+  /// clones the ground truth; if base and query are CPU-accessible, finds for every query how far the ground-truth
+  /// prefix extends over distance ties (<= 1e-6) behind rank 1 and rank KQuery (eval.cpp:88-174)
+  Evaluator(const GenericDataset& base, const GenericDataset& query, const Dataset<KeyT>& gt_in, uint32_t KQuery_,
+            DistanceMeasure measure_)
+      : KQuery{KQuery_}, measure{measure_}, gt{gt_in.clone()}
+  {
+    if (!base.N || !query.N) return;                                   // no duplicate information
+    if (!base.isCPUAccessible() || !query.isCPUAccessible()) return;   // ditto
+    if (!gt_in.isCPUAccessible()) throw std::runtime_error("Ground truth data needs to be given on the CPU for evaluation.");
+    if (base.type != query.type) throw std::invalid_argument("base and query have different data types");
+    if (base.type != DataType::FLOAT && base.type != DataType::UINT8) throw std::runtime_error("unsupported data type");
+    const bool is_float = base.type == DataType::FLOAT;
+    const auto bf = base.reinterpret<float>(), qf = query.reinterpret<float>();
+    const auto bu = base.reinterpret<uint8_t>(), qu = query.reinterpret<uint8_t>();
+    const size_t Db = base.D;
+    auto value = [&](bool of_base, size_t row, size_t d) -> ValueT {
+      const size_t i = row * Db + d;
+      return is_float ? static_cast<ValueT>(of_base ? bf[i] : qf[i]) : static_cast<ValueT>(of_base ? bu[i] : qu[i]);
+    };
+    // eval.cpp:37-65 (float accumulation in index order; the cosine b_norm is computed from `a` there, too)
+    auto dist_to_query = [&](size_t base_idx, size_t query_idx) -> ValueT {
+      if (base_idx >= base.N) throw std::out_of_range("ground truth index out of range");
+      ValueT acc = 0.0f, a_norm = 0.0f, b_norm = 0.0f;
+      for (size_t d = 0; d < Db; ++d) {
+        const ValueT a = value(true, base_idx, d), b = value(false, query_idx, d);
+        if (measure == DistanceMeasure::Euclidean) acc += (a - b) * (a - b);
+        else {
+          acc += a * b;
+          a_norm += a * a;
+          b_norm += a * a;
+        }
+      }
+      if (measure == DistanceMeasure::Euclidean) return std::sqrt(acc);
+      return (a_norm * b_norm > 0.0f) ? std::fabs(1.0f - acc / std::sqrt(a_norm * b_norm)) : 1.0f;
+    };
+    constexpr float Epsilon = 0.000001f;
+    const uint32_t GD = gt.D;
+    gt_duplicates.top1DuplicateEnd.reserve(query.N);
+    gt_duplicates.topKDuplicateEnd.reserve(query.N);
+    for (uint32_t n = 0; n < query.N; ++n) {
+      const KeyT* row = gt.data() + static_cast<size_t>(n) * GD;
+      auto run_after = [&](uint32_t anchor_rank, uint32_t first) {
+        const ValueT anchor = dist_to_query(static_cast<size_t>(row[anchor_rank]), n);
+        uint32_t len = 0;
+        for (uint32_t k = first; k < GD; ++k) {
+          if (dist_to_query(static_cast<size_t>(row[k]), n) - anchor > Epsilon) break;
+          ++len;
+        }
+        return len;
+      };
+      gt_duplicates.top1DuplicateEnd.push_back(1 + run_after(0, 1));
+      gt_duplicates.topKDuplicateEnd.push_back(KQuery <= GD ? KQuery + run_after(KQuery - 1, KQuery) : GD);
+    }
+  }
+
+  [[nodiscard]] Evaluation evaluateResults(const Dataset<KeyT>& results)
+  {
+    if (!gt.D) throw std::runtime_error("No ground truth data loaded. cannot compute accuracy.");
+    if (gt.N < results.N) throw std::out_of_range("more result rows than ground truth rows");
+    if (!results.isCPUAccessible()) throw std::runtime_error("Results need to be given on the CPU for evaluation.");
+    const bool has_dup = !gt_duplicates.top1DuplicateEnd.empty() && !gt_duplicates.topKDuplicateEnd.empty();
+    uint32_t c1 = 0, c1_dup = 0, cK = 0, cK_dup = 0, rK = 0, rK_dup = 0;
+    for (uint32_t n = 0; n < results.N; ++n) {
+      const uint32_t endTop1 = has_dup ? gt_duplicates.top1DuplicateEnd.at(n) : 1;
+      const uint32_t endTopK = has_dup ? gt_duplicates.topKDuplicateEnd.at(n) : KQuery;
+      if (endTopK > gt.D) throw std::out_of_range("ground truth has fewer than KQuery columns");
+      const KeyT* g = gt.data() + static_cast<size_t>(n) * gt.D;
+      for (uint32_t kr = 0; kr < KQuery; ++kr) {
+        const KeyT q = results[static_cast<size_t>(n) * KQuery + kr];
+        for (uint32_t kg = 0; kg < endTopK; ++kg) {  // eval.cpp:206-227: every match counts (no early exit)
+          if (q != g[kg]) continue;
+          if (kg == 0) {
+            c1 += (kr == 0);
+            rK += (kg < KQuery);
+            ++rK_dup;
+          }
+          if (kg < endTop1) c1_dup += (kr == 0);
+          cK += (kg < KQuery);
+          ++cK_dup;
+        }
+      }
+    }
+    const float inv_q = 1.0f / static_cast<float>(results.N);
+    const float inv_r = 1.0f / static_cast<float>(results.N * KQuery);
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    Evaluation e;
+    e.KQuery = KQuery;
+    e.c1 = static_cast<float>(c1) * inv_q;
+    e.c1_dup = has_dup ? static_cast<float>(c1_dup) * inv_q : nan;
+    e.cKQuery = static_cast<float>(cK) * inv_r;
+    e.cKQuery_dup = has_dup ? static_cast<float>(cK_dup) * inv_r : nan;
+    e.rKQuery = static_cast<float>(rK) * inv_q;
+    e.rKQuery_dup = has_dup ? static_cast<float>(rK_dup) * inv_q : nan;
+    return e;
+  }
 };
 
 /// device-side view of one shard's graph blob (include/ggnn/base/graph.h:36-72)
@@ -265,13 +583,13 @@ class GGNN {
 
   void setBase(GenericDataset&& b)
   {
+    check_base(b);
     owned_base = std::move(b);
-    setBaseReference(owned_base);
+    base = &owned_base;
   }
   void setBaseReference(const GenericDataset& b)
   {
-    if (!shards.empty()) throw std::runtime_error("The base cannot be changed after the graph has been set up.");
-    if (b.D < MIN_D || b.D > MAX_D) throw std::out_of_range("unsupported dimension");
+    check_base(b);
     base = &b;
   }
   void setBaseReference(GenericDataset&&) = delete;
@@ -325,7 +643,7 @@ class GGNN {
                               DistanceMeasure measure = DistanceMeasure::Euclidean)
   {
     if (shards.empty()) throw std::runtime_error("There is no graph to query.");
-    if (query.D != base->D) throw std::out_of_range("query dimension does not match the base");
+    check_query(query, "unsupported datatype for query");
     const uint32_t n_gpus = static_cast<uint32_t>(gpu_ids.size());
     if (return_results_on_gpu && n_gpus > 1)
       throw std::runtime_error("Returning query results on GPU is only possible when using a single GPU.");
@@ -333,19 +651,13 @@ class GGNN {
     std::vector<Dataset<KeyT>> ids(n_gpus);
     std::vector<Dataset<ValueT>> dists(n_gpus);
     std::vector<Dataset<float>> q_dev(n_gpus);
-    std::vector<Dataset<KeyT>> merged_i(n_gpus);
-    std::vector<Dataset<ValueT>> merged_d(n_gpus);
     // launch everything asynchronously on every GPU first
     for (uint32_t gi = 0; gi < n_gpus; ++gi) {
       const int gpu = gpu_ids[gi];
       detail::DeviceGuard g(gpu);
       cudaStream_t stream = shards[gi * spg].stream;
-      const float* dq = query.data();
-      if (!(query.isGPUAccessible() && query.gpu_id == gpu)) {
-        q_dev[gi] = Dataset<float>::emptyOnGPU(query.N, query.D, gpu);
-        detail::cuda_check(cudaMemcpyAsync(q_dev[gi].data(), query.data(), query.size_bytes(), cudaMemcpyDefault, stream), "cudaMemcpyAsync(query)");
-        dq = q_dev[gi].data();
-      }
+      q_dev[gi] = float_on_gpu(query, gpu, stream);
+      const float* dq = q_dev[gi].data();
       ids[gi] = Dataset<KeyT>::emptyOnGPU(Nq, KQuery * spg, gpu);
       dists[gi] = Dataset<ValueT>::emptyOnGPU(Nq, KQuery * spg, gpu);
       for (uint32_t s = 0; s < spg; ++s) {
@@ -364,12 +676,13 @@ class GGNN {
         detail::abi_check(ggnn_b200_query(&p, Nq, stream));
       }
       if (spg > 1) {  // replaces gpu_instance.cu:745-790
-        merged_i[gi] = Dataset<KeyT>::emptyOnGPU(Nq, KQuery, gpu);
-        merged_d[gi] = Dataset<ValueT>::emptyOnGPU(Nq, KQuery, gpu);
+        Dataset<KeyT> mi = Dataset<KeyT>::emptyOnGPU(Nq, KQuery, gpu);
+        Dataset<ValueT> md = Dataset<ValueT>::emptyOnGPU(Nq, KQuery, gpu);
         detail::abi_check(ggnn_b200_merge_topk(ids[gi].data(), dists[gi].data(), spg, KQuery, static_cast<size_t>(KQuery) * spg,
-                                               KQuery, Nq, KQuery, 0, merged_i[gi].data(), merged_d[gi].data(), stream));
-        ids[gi] = std::move(merged_i[gi]);
-        dists[gi] = std::move(merged_d[gi]);
+                                               KQuery, Nq, KQuery, 0, mi.data(), md.data(), stream));
+        detail::cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");  // the inputs are freed below
+        ids[gi] = std::move(mi);
+        dists[gi] = std::move(md);
       }
     }
     Results out;
@@ -379,7 +692,7 @@ class GGNN {
       out.ids = std::move(ids[0]);
       out.dists = std::move(dists[0]);
     }
-    else {  // replaces ResultMerger::merge (result_merger.cpp:51-149): peer copies + one merge kernel on GPU 0
+    else {  // replaces ResultMerger::merge (result_merger.cpp:51-149): peer copies + one merge kernel on the first GPU
       const int g0 = gpu_ids[0];
       Dataset<KeyT> all_i = Dataset<KeyT>::emptyOnGPU(static_cast<uint64_t>(n_gpus) * Nq, KQuery, g0);
       Dataset<ValueT> all_d = Dataset<ValueT>::emptyOnGPU(static_cast<uint64_t>(n_gpus) * Nq, KQuery, g0);
@@ -405,28 +718,23 @@ class GGNN {
   {
     if (!base) throw std::runtime_error("The base needs to be set before running a brute-force query.");
     if (gpu_ids.size() > 1) throw std::runtime_error("bfQuery supports only a single GPU.");  // ggnn.cu:338-339
+    check_query(query, "unsupported datatype for brute-force query");
     const int gpu = gpu_ids[0];
     detail::DeviceGuard g(gpu);
-    Dataset<float> b_dev, q_dev;
-    const float* db = base->data();
-    if (!shards.empty() && shards.size() == 1) db = shards[0].base.data();
-    else if (!(base->isGPUAccessible() && base->gpu_id == gpu)) {
-      b_dev = Dataset<float>::emptyOnGPU(base->N, base->D, gpu);
-      detail::cuda_check(cudaMemcpy(b_dev.data(), base->data(), base->size_bytes(), cudaMemcpyDefault), "cudaMemcpy(base)");
+    Dataset<float> b_dev;
+    const float* db = nullptr;
+    if (shards.size() == 1) db = shards[0].base.data();
+    else {
+      b_dev = float_on_gpu(*base, gpu, nullptr);
       db = b_dev.data();
     }
-    const float* dq = query.data();
-    if (!(query.isGPUAccessible() && query.gpu_id == gpu)) {
-      q_dev = Dataset<float>::emptyOnGPU(query.N, query.D, gpu);
-      detail::cuda_check(cudaMemcpy(q_dev.data(), query.data(), query.size_bytes(), cudaMemcpyDefault), "cudaMemcpy(query)");
-      dq = q_dev.data();
-    }
+    Dataset<float> q_dev = float_on_gpu(query, gpu, nullptr);
     Results out;
     out.ids = Dataset<KeyT>::emptyOnGPU(query.N, KGT, gpu);
     out.dists = Dataset<ValueT>::emptyOnGPU(query.N, KGT, gpu);
     ggnn_b200_bf_query_params p{};
     p.D = base->D; p.measure = static_cast<int>(measure); p.KQuery = KGT; p.N_base = static_cast<int32_t>(base->N);
-    p.d_base = db; p.d_query = dq; p.d_query_results = out.ids.data(); p.d_query_results_dists = out.dists.data();
+    p.d_base = db; p.d_query = q_dev.data(); p.d_query_results = out.ids.data(); p.d_query_results_dists = out.dists.data();
     p.workspace_bytes = ggnn_b200_bf_query_workspace_bytes(p.D, p.measure, KGT, static_cast<uint32_t>(base->N), static_cast<uint32_t>(query.N));
     if (p.workspace_bytes) detail::cuda_check(cudaMalloc(&p.d_workspace, p.workspace_bytes), "cudaMalloc(bf workspace)");
     const int rc = ggnn_b200_bf_query(&p, static_cast<uint32_t>(query.N), nullptr);
@@ -462,10 +770,51 @@ class GGNN {
     return h;
   }
 
+  void check_base(const GenericDataset& b) const
+  {
+    if (!shards.empty()) throw std::runtime_error("The base cannot be changed after the graph has been set up.");
+    if (b.type != DataType::FLOAT && b.type != DataType::UINT8) throw std::runtime_error("unsupported datatype for base");  // ggnn.cu:456-491
+    if (b.D < MIN_D || b.D > MAX_D) throw std::out_of_range("unsupported dimension");
+  }
+  void check_query(const GenericDataset& q, const char* what) const
+  {
+    if (q.type != DataType::FLOAT && q.type != DataType::UINT8) throw std::runtime_error(what);
+    // the reference CHECK-aborts here (ggnn.cu:524-540)
+    if (q.type != base->type) throw std::runtime_error("query data type does not match base data type");
+    if (q.D != base->D) throw std::out_of_range("query dimension does not match the base");
+  }
+
+  /// rows [from, from + num) of `src` (float or uint8, anywhere) as fp32 on `gpu`; uint8 is widened on the device.
+  /// Already-resident float data is referenced, not copied.  The current device must be `gpu`.
+  static Dataset<float> float_on_gpu(const GenericDataset& src, int gpu, cudaStream_t stream, uint64_t from = 0,
+                                     uint64_t num = std::numeric_limits<uint64_t>::max())
+  {
+    if (num == std::numeric_limits<uint64_t>::max()) num = src.N - from;
+    GenericDataset rows = src.referenceRange(from, num);
+    const bool resident = rows.isGPUAccessible() && (rows.gpu_id == gpu || rows.location == DataLocation::MANAGED);
+    if (rows.type == DataType::FLOAT) {
+      if (resident) return Dataset<float>{std::move(rows)};
+      Dataset<float> d = Dataset<float>::emptyOnGPU(num, src.D, gpu);
+      detail::cuda_check(cudaMemcpyAsync(d.data(), static_cast<const void*>(rows), rows.required_size_bytes(), cudaMemcpyDefault, stream), "cudaMemcpyAsync(float rows)");
+      return d;
+    }
+    Dataset<float> d = Dataset<float>::emptyOnGPU(num, src.D, gpu);
+    Dataset<uint8_t> staged;
+    const uint8_t* u8 = static_cast<const uint8_t*>(static_cast<const void*>(rows));
+    if (!resident) {
+      staged = Dataset<uint8_t>::emptyOnGPU(num, src.D, gpu);
+      detail::cuda_check(cudaMemcpyAsync(staged.data(), u8, rows.required_size_bytes(), cudaMemcpyDefault, stream), "cudaMemcpyAsync(uint8 rows)");
+      u8 = staged.data();
+    }
+    detail::abi_check(ggnn_b200_widen_u8(u8, d.data(), rows.numel(), stream));
+    detail::cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");  // `staged` is freed on return
+    return d;
+  }
+
   // src/ggnn/base/ggnn.cu:154-203
   void prepare(uint32_t KBuild)
   {
-    if (!base || !base->data()) throw std::runtime_error("The base needs to be set before building a graph.");
+    if (!base || !static_cast<const void*>(*base)) throw std::runtime_error("The base needs to be set before building a graph.");
     if (KBuild < MIN_KBUILD || KBuild > MAX_KBUILD) throw std::out_of_range("KBuild out of range");
     if (!shards.empty()) {
       if (cfg.KBuild != KBuild) throw std::runtime_error("graph already set up with a different KBuild");
@@ -489,9 +838,7 @@ class GGNN {
         sh.global_id = gi * spg + s;
         detail::cuda_check(cudaStreamCreate(&sh.stream), "cudaStreamCreate");
         detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&sh.work_counter), 16), "cudaMalloc");
-        sh.base = Dataset<float>::emptyOnGPU(n_shard, base->D, sh.gpu);
-        detail::cuda_check(cudaMemcpyAsync(sh.base.data(), base->data() + static_cast<size_t>(sh.global_id) * n_shard * base->D,
-                                           sh.base.size_bytes(), cudaMemcpyDefault, sh.stream), "cudaMemcpyAsync(base shard)");
+        sh.base = float_on_gpu(*base, sh.gpu, sh.stream, static_cast<uint64_t>(sh.global_id) * n_shard, n_shard);
         sh.graph.config = cfg;
         sh.graph.offsets = off;
         sh.graph.memory = Dataset<uint8_t>::emptyOnGPU(off.total, 1, sh.gpu);

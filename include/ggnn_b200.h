@@ -174,6 +174,14 @@ int ggnn_b200_merge_topk(const int32_t* d_ids, const float* d_dists, uint32_t n_
                          int64_t id_offset_per_list, int32_t* d_out_ids, float* d_out_dists,
                          ggnn_b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * uint8 base / query vectors (the reference's BaseT = uint8_t instantiation, include/ggnn/base/lib.h:26-28).
+ * Every distance of the reference is computed on static_cast<ValueT>(value) (include/ggnn/cuda_utils/
+ * distance.cuh:104-148), so widening the vectors to fp32 once on the device and running the fp32 kernels gives
+ * bit-identical results.  d_dst[i] = (float)d_src[i] for i < count.
+ * ---------------------------------------------------------------------------------------------- */
+int ggnn_b200_widen_u8(const uint8_t* d_src, float* d_dst, size_t count, ggnn_b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

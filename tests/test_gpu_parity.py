@@ -171,6 +171,85 @@ def test_query_bit_exact_vs_oracle_on_oracle_built_graph(K, tau, max_it, D, meas
     assert np.array_equal(st, o_st)  # pops / distance evaluations (roofline accounting)
 
 
+@pytest.mark.parametrize("K,max_it,D,measure,kind,Nq", [
+    (150, 400, 128, 0, "uniform", 60),    # sorted 192: register lists, 6 slots per lane
+    (239, 400, 64, 0, "uniform", 40),     # sorted 256: the largest register-resident variant
+    (240, 400, 128, 0, "uniform", 40),    # sorted 288 -> lists in shared memory
+    (500, 300, 96, 1, "normal", 24),      # cache 544 (not a power of two), visited ring of 32 entries wraps
+    (1000, 2000, 32, 0, "uniform", 12),   # cache 2048, block_dim_x 128
+    (2999, 400, 128, 0, "uniform", 6),    # K == N - 1: the best list never fills
+])
+def test_query_large_k_bit_exact_vs_oracle(K, max_it, D, measure, kind, Nq):
+    """KQuery beyond the register-resident lists (the reference allows KQuery <= 6000, query_kernels.cu:63-69):
+    same ids, distances and counters as the reference's block loop (oracle)"""
+    N = 3000
+    base, query = gen_data(N, Nq, D, seed=K + D, kind=kind)
+    rng = np.random.default_rng(5).random(N + 1000, dtype=np.float32) * 0.999 + 0.0005
+    gr = O.build_graph(O.graph_config(N, D, 24), base, 0.5, rng, 0, measure)
+    ids, dists, st = c_query(base, query, gr.layer_graph(0), gr.start_points(), gr.nn1_stats, K, 1.2, max_it, measure,
+                             stats=True)
+    o_ids, o_d, o_st = O.query(base, query, gr.layer_graph(0), gr.start_points(), gr.nn1_stats, K, 1.2, max_it, measure,
+                               with_stats=True)
+    assert np.array_equal(ids, o_ids)
+    assert np.array_equal(dists, o_d)
+    assert np.array_equal(st, o_st)
+
+
+def test_query_k_6000_runs_and_is_sorted():
+    """the API maximum (KQuery 6000 -> sorted 6048, cache 6080, block_dim_x 512): finishes, sorted, valid ids,
+    distances equal a re-computation in the reference's summation order for the virtual 512-thread block"""
+    N, Nq, D, K = 8000, 4, 64, 6000
+    base, query = gen_data(N, Nq, D, seed=3)
+    rng = np.random.default_rng(5).random(N + 3000, dtype=np.float32) * 0.999 + 0.0005
+    gr = O.build_graph(O.graph_config(N, D, 24), base, 0.5, rng, 0, 0)
+    ids, dists = c_query(base, query, gr.layer_graph(0), gr.start_points(), gr.nn1_stats, K, 2.0, 400, 0)
+    o_ids, o_d = O.query(base, query, gr.layer_graph(0), gr.start_points(), gr.nn1_stats, K, 2.0, 400, 0)
+    assert np.array_equal(ids, o_ids) and np.array_equal(dists, o_d)
+    filled = ids >= 0
+    assert filled.any() and np.all(np.diff(np.where(filled, dists, np.inf), axis=1) >= 0)
+
+
+@pytest.mark.parametrize("K,D,measure,kind", [(120, 64, 0, "uniform"), (161, 32, 1, "normal")])
+def test_build_large_kbuild_bit_exact_vs_oracle(K, D, measure, kind):
+    """KBuild up to the reference's effective maximum (161: sym sorted_size < 128).  The graph state comes from our
+    own full build (the oracle's sequential sym is minutes of CPU at this K); on that state `top` and `merge` are
+    compared with the oracle stage by stage."""
+    N, tau = 2500, 0.5
+    base, _ = gen_data(N, 1, D, seed=K, kind=kind)
+    cfg_o = O.graph_config(N, D, K)
+    g = ggnn.GGNN()
+    g.set_base(torch.from_numpy(base))
+    g.build(K, tau, 1, ggnn.DistanceMeasure(measure))
+    state = g.get_graph(0).blob.cpu().numpy().copy()
+    q = torch.from_numpy(base[:64].copy())
+    ids, _ = g.query(q, 10, 1.0, 400, ggnn.DistanceMeasure(measure))
+    assert (ids[:, 0].cpu().numpy() == np.arange(64)).mean() > 0.9   # the graph is usable
+    lib = _lib.lib()
+    b = dev(base)
+    nn1_d = torch.zeros(N, dtype=torch.float32, device="cuda")
+    gbuf = torch.zeros((N, K), dtype=torch.int32, device="cuda")
+    for layer in (1, 0):
+        want = O.Graph(cfg_o, state.copy())
+        nn1_o = O.top(want, base, layer, measure)
+        dg = DevGraph(cfg_o, state)
+        _lib.check(lib.ggnn_b200_top(C.byref(dg.cfg), ptr(b), measure, layer, ptr(dg.blob), ptr(nn1_d), stream()))
+        torch.cuda.synchronize()
+        assert np.array_equal(dg.host(cfg_o).layer_graph(layer), want.layer_graph(layer)), f"top {layer}"
+        assert np.array_equal(nn1_d.cpu().numpy()[:cfg_o.Ns[layer]], nn1_o)
+    for top, btm in ((3, 2), (2, 0)):
+        want = O.Graph(cfg_o, state.copy())
+        nn1_m = O.merge(want, base, top, btm, tau, measure)
+        dg = DevGraph(cfg_o, state)
+        _lib.check(lib.ggnn_b200_merge(C.byref(dg.cfg), ptr(b), measure, tau, top, btm, ptr(dg.blob), ptr(gbuf), ptr(nn1_d), stream()))
+        torch.cuda.synchronize()
+        assert np.array_equal(dg.host(cfg_o).layer_graph(btm), want.layer_graph(btm)), f"merge {top}->{btm}"
+        if btm == 0:
+            assert np.array_equal(nn1_d.cpu().numpy(), nn1_m)
+    # beyond the reference's own CHECK (sym_query_layer.cuh:46): an error, not a crash
+    cfg_bad = _lib.graph_config(N, D, 200)
+    assert lib.ggnn_b200_top(C.byref(cfg_bad), ptr(b), measure, 0, ptr(dg.blob), ptr(nn1_d), stream()) == _lib.ERR_INVALID
+
+
 def test_query_edge_cases_vs_oracle():
     """ragged / extreme shapes: one query, zero queries, k_build > 32 (two adjacency chunks per anchor), tiny base,
     D = 4, long rows (D = 2048 -> one warp per CTA), graph rows containing -1 and duplicate ids"""
@@ -419,18 +498,62 @@ def test_full_size_properties(big):
 # ------------------------------------------------------------------------------------------------
 # C++ host API (include/ggnn/ggnn.hpp)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("exe", ["ggnn_main", "ref_ggnn_main_on_b200"])
-def test_cpp_api_example_programs_run(exe):
-    """examples/ggnn_main: our example; ref_ggnn_main_on_b200: the REFERENCE's unmodified example program
-    (examples/cpp-and-cuda/ggnn_main.cpp) compiled against include/ggnn/base/ggnn.cuh of this repo"""
+def _example(exe):
     import os
-    import subprocess
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", exe)
     if not os.path.exists(path):
         pytest.skip(f"{exe} not built (needs __graft_entry__.build() in the container that has the sources)")
-    p = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    return path
+
+
+@pytest.mark.parametrize("exe", ["ggnn_main", "ref_ggnn_main_on_b200", "ref_ggnn_main_gpu_data_on_b200",
+                                 "ref_ggnn_main_multi_gpu_on_b200"])
+def test_cpp_api_example_programs_run(exe):
+    """examples/ggnn_main: our example; ref_*_on_b200: the REFERENCE's unmodified example programs
+    (examples/cpp-and-cuda/{ggnn_main.cpp, ggnn_main_gpu_data.cu, ggnn_main_multi_gpu.cpp}) compiled against
+    include/ggnn/base/ggnn.cuh of this repo"""
+    import subprocess
+    if "multi_gpu" in exe and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (ggnn_main_multi_gpu.cpp:62 setGPUs({0, 1}))")
+    p = subprocess.run([_example(exe)], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "base[" in p.stdout.lower() or "recall" in p.stdout.lower()
+
+
+@pytest.mark.parametrize("ext", ["fvecs", "bvecs"])
+def test_reference_benchmark_program_runs_on_our_library(tmp_path, ext):
+    """the reference's unmodified ggnn_benchmark.cpp (fvecs/bvecs in, build or load, ground truth by bfQuery or from
+    an ivecs file, Evaluator, tau sweep) on include/ggnn + libggnn_b200.so; the ground truth it exports equals
+    bf_query of the Python API bit for bit, a second run (graph + ground truth loaded from disk) reports the same"""
+    import os
+    import re
+    import subprocess
+    exe = _example("ref_ggnn_benchmark_on_b200")
+    rng = np.random.default_rng(11)
+    N, Nq, D = 20000, 500, 128
+    latent = rng.standard_normal((N + Nq, 8)).astype(np.float32) @ rng.standard_normal((8, D)).astype(np.float32)
+    data = np.clip(np.rint(latent * 12 + 128 + rng.standard_normal((N + Nq, D))), 0, 255)
+    data = data.astype(np.uint8) if ext == "bvecs" else data.astype(np.float32)
+    from tests.test_host_logic import _write_vecs
+    bp, qp, gp = (os.path.join(tmp_path, f) for f in (f"base.{ext}", f"query.{ext}", "gt.ivecs"))
+    _write_vecs(bp, data[:N])
+    _write_vecs(qp, data[N:])
+    gdir = os.path.join(tmp_path, "graph")
+    os.makedirs(gdir)
+    cmd = [exe, f"--base={bp}", "--query", qp, f"--gt={gp}", f"--graph_dir={gdir}", "--k_build=24", "--max_iterations", "400"]
+    runs = []
+    for _ in range(2):
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout + p.stderr
+        runs.append([float(x) for x in re.findall(r"c@10: ([0-9.]+)", p.stdout + p.stderr)])
+        assert os.path.exists(os.path.join(gdir, "part_0.ggnn")) and os.path.exists(gp)
+    assert len(runs[0]) == 4 and runs[0] == runs[1]          # tau_query 0.34 / 0.41 / 0.51 / 0.64
+    assert runs[0][-1] > 0.95 and runs[0][-1] >= runs[0][0]
+    gt = np.fromfile(gp, dtype=np.int32).reshape(Nq, 101)[:, 1:]
+    g = ggnn.GGNN()
+    g.set_base(torch.from_numpy(data[:N]))
+    ids, _ = g.bf_query(torch.from_numpy(data[N:]), 100)
+    assert np.array_equal(ids.cpu().numpy(), gt)
 
 
 def test_uint8_base_vectors_match_oracle_on_widened_values():

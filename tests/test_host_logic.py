@@ -90,6 +90,56 @@ def test_fvecs_roundtrip(tmp_path):
     assert torch.equal(ggnn.IntDataset.load(p2).tensor, i)
 
 
+def _write_vecs(path, arr):
+    """[int32 D][D values] per row (src/ggnn/base/dataset.cu:204-215)"""
+    arr = np.ascontiguousarray(arr)
+    with open(path, "wb") as f:
+        for row in arr:
+            f.write(np.int32(arr.shape[1]).tobytes())
+            f.write(row.tobytes())
+
+
+def test_cpp_host_api_datasets_io_and_evaluator(tmp_path):
+    """include/ggnn/ggnn.hpp on the CPU: dataset factories / type erasure / [fbi]vecs IO / argument checks inside the
+    C++ test program; its Evaluator output must equal the oracle's restatement of eval.cpp for float and uint8 data"""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(tmp_path, "host_api_test")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", f"-I{root}/include", "-I/usr/local/cuda/include",
+                           f"{root}/tests/cpp/host_api_test.cpp", f"-L{root}/ggnn_b200", "-lggnn_b200",
+                           "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{root}/ggnn_b200", "-o", exe])
+    rng = np.random.default_rng(7)
+    base_u8 = rng.integers(0, 256, (300, 16), dtype=np.uint8)
+    base_u8[10] = base_u8[11]
+    base_u8[12] = base_u8[11]                  # a run of exact duplicates
+    query_u8 = rng.integers(0, 256, (25, 16), dtype=np.uint8)
+    query_u8[0] = base_u8[10]
+    base = (base_u8.astype(np.float32) / 255).astype(np.float32)
+    query = (query_u8.astype(np.float32) / 255).astype(np.float32)
+    K = 10
+    gt, _ = O.bf_query(base, query, 20)
+    res = gt[:, :K].copy()
+    res[::3, 2] = 299
+    res[0, 0] = gt[0, 1]
+    res[1, 5] = res[1, 4]                      # the same id twice in one result row: every match counts (eval.cpp:206-227)
+    for name, arr in (("base.fvecs", base), ("query.fvecs", query), ("base.bvecs", base_u8), ("query.bvecs", query_u8),
+                      ("gt.ivecs", gt.astype(np.int32)), ("res.ivecs", res.astype(np.int32))):
+        _write_vecs(os.path.join(tmp_path, name), arr)
+    out = json.loads(subprocess.check_output([exe, str(tmp_path), str(K)]))
+    assert out["base"] == [300, 16] and out["gt"] == [25, 20]
+    for tag, b, q in (("float", base, query), ("uint8", base_u8.astype(np.float32), query_u8.astype(np.float32))):
+        for measure in (0, 1):
+            o = O.evaluate(gt, res, K, b, q, measure)
+            got = out[f"{tag}_{measure}"]
+            for k in o:
+                assert got[k] == pytest.approx(o[k], abs=1e-6), (tag, measure, k)
+    o = O.evaluate(gt, res, K)
+    assert out["nodup"]["cK"] == pytest.approx(o["cK"], abs=1e-6) and out["nodup"]["c1_dup"] == -1
+    # files written by the C++ side are readable by the Python mirror
+    assert torch.equal(ggnn.FloatDataset.load(os.path.join(tmp_path, "rt.fvecs")).tensor, torch.arange(12.).view(3, 4))
+
+
 def test_oracle_merge_semantics():
     ids = np.array([[[0, 1, 2]], [[0, 1, 2]]], np.int32)               # 2 partitions, 1 query, K_in 3
     d = np.array([[[0.1, 0.4, 0.9]], [[0.2, 0.4, 0.5]]], np.float32)
