@@ -573,6 +573,8 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const TcRerankArgs a)
   ws.parity = 0;
   ws.stage_rows = 32;
   ws.stage_mode = 0;
+  ws.tmap = nullptr;
+  ws.pad_row = 0;
   if (lane == 0) mbar_init(ws.bar, 1);
   mbar_fence_init();
   __syncwarp();

@@ -60,6 +60,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
   }
 }
+// same, but traps instead of spinning forever (used by the tensor-map staging mode: a malformed descriptor would
+// otherwise never complete the transaction count)
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok = 0;
+  const uint32_t a = smem_u32(bar);
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (spins > (1u << 24)) __trap();
+  }
+}
 // one row: global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
@@ -67,6 +84,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// four rows of a 2-D tensor (row-major base vectors, box = one whole row) by row index in ONE instruction
+// (TMA tile::gather4, sm_100): a quarter of the issue overhead of one bulk copy per row
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const void* tmap, int r0, int r1, int r2, int r3, uint64_t* bar)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // 16-byte asynchronous copy global -> shared (SASS: LDGSTS.E.BYPASS.128), one warp instruction moves a
@@ -78,6 +106,33 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void cp_async_wait_all()
 {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed fp32 arithmetic (Blackwell FFMA2 / FADD2): two independent IEEE fma.rn / add.rn per instruction, each
+// element rounded exactly like the scalar instruction -- used to evaluate two base rows at once
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -46,7 +46,7 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   const uint32_t row_bytes = D * 4;
   const uint32_t vcap = cache > sorted ? cache - sorted : 0;
   pl.ring_cap = (vcap && vcap < max_pops) ? vcap : 0;
-  pl.hsize = cache ? std::max(64u, 2u * bit_ceil_u32(std::max(1u, max_pops))) : 0;
+  pl.hsize = cache ? std::max(64u, bit_ceil_u32(max_pops + max_pops / 4 + 1)) : 0;  // see query.cu
   const uint32_t fixed = (need_sq ? align_up(row_bytes, 16) : 0) + (need_half ? align_up(row_bytes, 16) : 0) +
                          align_up(sorted * 4, 16) + pl.hsize * 4 + align_up(pl.ring_cap * 4, 16) + 32;
   const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / CW + 1)) / target_warps_per_sm;
@@ -56,6 +56,7 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   if (pl.stage_rows % 8 || pl.stage_rows == 0 || pl.stage_rows > 32) pl.stage_rows = rows;
   rows = pl.stage_rows;
   pl.stage_mode = (D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 0);  // rows must be 16-byte multiples to be staged
+  if (pl.stage_mode == 3) pl.stage_mode = 0;  // gather4 staging is wired up for the query kernel only
   uint32_t off = align_up(rows * row_bytes, 16);
   pl.off_sq = off;
   off += need_sq ? align_up(row_bytes, 16) : 0;
@@ -85,6 +86,8 @@ __device__ __forceinline__ void init_warp_smem(WarpSmem& ws, VisitedSet& V, unsi
   ws.parity = 0;
   ws.stage_rows = pl.stage_rows;
   ws.stage_mode = pl.stage_mode;
+  ws.tmap = nullptr;
+  ws.pad_row = 0;
   if (lane_id() < 4) mbar_init(&ws.bar[lane_id()], 1);
   mbar_fence_init();
   __syncwarp();

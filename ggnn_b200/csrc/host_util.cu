@@ -1,4 +1,6 @@
 #include "host_util.h"
+
+#include <cuda.h>
 #include "../../include/ggnn_b200.h"
 
 #include <cstdio>
@@ -49,6 +51,38 @@ const DeviceInfo& device_info()
     have[dev] = true;
   }
   return infos[dev];
+}
+
+int make_row_gather_tensor_map(TensorMapStorage* out, const float* d_base, uint64_t rows, uint32_t cols)
+{
+  static_assert(sizeof(CUtensorMap) == sizeof(TensorMapStorage), "CUtensorMap is 128 bytes");
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+  });
+  if (!encode) return set_error(GGNN_B200_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  if (cols == 0 || cols > 256 || cols % 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "row gather tensor map needs D % 4 == 0 and D <= 256");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * sizeof(float)};
+  const cuuint32_t box[2] = {cols, 1};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_base), dims,
+                            strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+    return set_error(GGNN_B200_ERR_UNSUPPORTED, msg);
+  }
+  return 0;
 }
 
 uint32_t env_u32(const char* name, uint32_t dflt)

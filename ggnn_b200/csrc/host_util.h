@@ -19,6 +19,13 @@ const DeviceInfo& device_info();  // of the current device (cached per device)
 
 uint32_t env_u32(const char* name, uint32_t dflt);
 
+// CUtensorMap (128 bytes, 64-byte aligned) of a row-major fp32 matrix [rows, cols] whose box is one whole row:
+// the operand of TMA tile::gather4 row gathers.  Returns 0 or an error code (message set).
+struct alignas(64) TensorMapStorage {
+  unsigned char bytes[128];
+};
+int make_row_gather_tensor_map(TensorMapStorage* out, const float* d_base, uint64_t rows, uint32_t cols);
+
 inline uint32_t bit_ceil_u32(uint32_t v)
 {
   if (v <= 1) return 1;

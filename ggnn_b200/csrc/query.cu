@@ -26,11 +26,13 @@ struct QueryArgs {
   uint32_t ring_cap;   // 0 = ring mirror not needed
   uint32_t off_sq, off_sorted, off_hash, off_ring, off_bar;  // byte offsets in the per-warp block
   uint32_t off_lists;  // SmemLists backing store (sorted_size > 256 only)
+  int32_t pad_row;     // gather4 staging: row index that pads a group of four (see traverse.cuh)
+  TensorMapStorage tmap;  // gather4 staging (stage_mode 3): tensor map of the base
 };
 
 // LT = WarpLists<NS> (best list + prioQ in registers, sorted_size <= 256) or SmemLists (anything larger)
-template <class LT, bool FAST, int NI>
-__global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryArgs a)
+template <class LT, bool FAST, int NI, bool G4 = false>
+__global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const __grid_constant__ QueryArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
@@ -46,6 +48,8 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
   ws.parity = 0;
   ws.stage_rows = a.stage_rows;
   ws.stage_mode = a.stage_mode;
+  ws.tmap = G4 ? &a.tmap : nullptr;
+  ws.pad_row = G4 ? a.pad_row : 0;
   if (lane < 4) mbar_init(&ws.bar[lane], 1);
   mbar_fence_init();
   __syncwarp();
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
     // query_layer.cu:55 fetch_unfiltered(d_starting_points, nullptr, S)
     for (uint32_t i = 0; i < p.num_starting_points; i += 32) {
       const int ck = (i + lane < p.num_starting_points) ? p.d_starting_points[i + lane] : EMPTY_KEY;
-      fetch<LT, FAST, NI, 1, false>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st, a.prefetch ? p.d_graph : nullptr,
+      fetch<LT, FAST, NI, 1, false, G4>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st, a.prefetch ? p.d_graph : nullptr,
                                     p.KBuild);
     }
 
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
         else
           ck = (i + lane < p.KBuild) ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane) : EMPTY_KEY;
         spec.key = EMPTY_KEY;
-        fetch<LT, FAST, NI, 1, true>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
+        fetch<LT, FAST, NI, 1, true, G4>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
                                      p.KBuild, use_spec ? &spec : nullptr);
       }
     }
@@ -131,10 +135,10 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const QueryAr
   }
 }
 
-template <class LT, bool FAST, int NI>
+template <class LT, bool FAST, int NI, bool G4 = false>
 static int launch(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream)
 {
-  auto kern = query_kernel<LT, FAST, NI>;
+  auto kern = query_kernel<LT, FAST, NI, G4>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(query_kernel)");
   kern<<<grid, a.warps_per_cta * 32, smem, stream>>>(a);
@@ -206,7 +210,13 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   const uint32_t row_bytes = p.D * 4;
   const uint32_t vcap = p.cache_size - p.sorted_size;
   a.ring_cap = (vcap < p.max_iterations) ? vcap : 0;
-  a.hsize = std::max(64u, 2u * bit_ceil_u32(std::max(1u, p.max_iterations)));
+  // visited hash: at most max_iterations keys are ever inserted; a power of two >= 1.25x that keeps probe sequences
+  // short in the worst case and the table small (more resident warps per SM: 0.70 -> 0.64 ms on the bench workload)
+  a.hsize = std::max(64u, bit_ceil_u32(p.max_iterations + p.max_iterations / 4 + 1));
+  {  // tuning override: any power of two that can never fill up (at most max_iterations keys are ever inserted)
+    const uint32_t hs = env_u32("GGNN_B200_QUERY_HASH_SLOTS", 0);
+    if (hs >= 64 && (hs & (hs - 1)) == 0 && hs > p.max_iterations) a.hsize = hs;
+  }
   const uint32_t sorted_mirror = smem_lists ? 128u : p.sorted_size * 4;  // SmemLists only need 32 ints of scratch
   const uint32_t lists_bytes = smem_lists ? p.sorted_size * 8 : 0;
   const uint32_t fixed = (fast ? 0 : align_up(row_bytes, 16)) + sorted_mirror + lists_bytes + a.hsize * 4 +
@@ -220,7 +230,15 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   rows = env_u32("GGNN_B200_QUERY_STAGE_ROWS", rows);
   if (rows % 8 || rows == 0 || rows > 32) return set_error(GGNN_B200_ERR_INVALID, "stage rows must be 8, 16, 24 or 32");
   a.stage_rows = rows;
-  a.stage_mode = (p.D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 0);  // rows must be 16-byte multiples to be staged
+  // rows must be 16-byte multiples to be staged; default: TMA gather4 (3) where a variant exists, else one bulk copy per row (0)
+  a.stage_mode = (p.D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 3);
+  if (a.stage_mode == 3) {  // TMA tile::gather4 row staging: register-resident fast kernels with pipelined 8-row groups only
+    if (fast && rows >= 16 && (NI == 3 || NI == 4)) {  // the instantiated gather4 variants
+      if (int rc = make_row_gather_tensor_map(&a.tmap, p.d_base, static_cast<uint64_t>(p.N_base), p.D)) return rc;
+      a.pad_row = env_u32("GGNN_B200_GATHER4_PAD_VALID", 0) ? 0 : p.N_base;  // out of bounds: zero fill, no memory traffic
+    }
+    else a.stage_mode = 0;
+  }
   a.prefetch = env_u32("GGNN_B200_QUERY_PREFETCH", 2);  // 0 off, 1 L2 prefetch of candidate rows, 2 speculative next-anchor row load
   uint32_t off = align_up(rows * row_bytes, 16);
   a.off_sq = off;
@@ -252,6 +270,15 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
 
 #define G200_LAUNCH(NS_, FAST_, NI_) return launch<WarpLists<NS_>, FAST_, NI_>(a, grid, smem, stream)
   if (smem_lists) return launch<SmemLists, false, 1>(a, grid, smem, stream);
+  if (a.stage_mode == 3) {
+    switch (NS * 10 + NI) {
+      case 13: return launch<WarpLists<1>, true, 3, true>(a, grid, smem, stream);
+      case 14: return launch<WarpLists<1>, true, 4, true>(a, grid, smem, stream);
+      case 23: return launch<WarpLists<2>, true, 3, true>(a, grid, smem, stream);
+      case 24: return launch<WarpLists<2>, true, 4, true>(a, grid, smem, stream);
+      default: return set_error(GGNN_B200_ERR_UNSUPPORTED, "no gather4 kernel variant");
+    }
+  }
   if (fast) {
     switch (NS * 10 + NI) {
       case 11: G200_LAUNCH(1, true, 1);

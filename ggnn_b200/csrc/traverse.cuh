@@ -6,6 +6,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef G200_PACKED_DIST
+#define G200_PACKED_DIST 1  // Euclidean distances of row pairs in packed fp32 (FFMA2 / FADD2)
+#endif
+
 namespace g200 {
 
 // per-warp shared-memory working set
@@ -18,6 +22,9 @@ struct WarpSmem {
   uint32_t stage_rows;  // multiple of 8
   uint32_t stage_mode;  // 0: one cp.async.bulk (TMA engine) per row; 1: 16-byte cp.async per lane (LDGSTS);
                         // 2: no staging -- rows are not 16-byte aligned (D % 4 != 0), distances read global memory
+                        // 3: TMA tile::gather4 -- four rows per instruction through a tensor map of the base
+  const void* tmap;     // CUtensorMap of the base ([N, D] fp32, box = one row) for stage_mode 3 (G4 kernels only)
+  int pad_row;          // row index used to fill a gather4 up to four rows (out of bounds -> zero fill, no traffic)
 };
 
 // Move rows [b0, b0+nb) of the candidate list (lane b0+r holds the base row index m of local row r) into
@@ -26,7 +33,7 @@ __device__ __forceinline__ void stage_rows_g2s(WarpSmem& ws, const float* __rest
 {
   const int lane = lane_id();
   const uint32_t row_bytes = D * 4u;
-  if (ws.stage_mode == 0) {
+  if (ws.stage_mode == 0 || ws.stage_mode == 3) {
     if (lane == 0) mbar_expect_tx(ws.bar, row_bytes * nb);
     __syncwarp();
     const int r = lane - b0;
@@ -61,6 +68,26 @@ __device__ __forceinline__ float dist8_fast(const float* __restrict__ rows, int 
 {
   const int lane = lane_id();
   constexpr int D = 32 * D32;
+  if (measure == 0 && NW == 1 && G200_PACKED_DIST) {
+    // one reference warp, Euclidean: rows (2p, 2p+1) advance together in packed fp32 (per element the same
+    // sub.rn + fma.rn chain over dims lane, lane+32, ... as the scalar code).  Always the whole group: rows >= nrows
+    // hold stale shared memory, their results are never used.
+    uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int c = 0; c < D32; ++c) {
+      const uint64_t q2 = pack2(q[c], q[c]);
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const float* rp = rows + (2 * pr) * D + 32 * c + lane;
+        const uint64_t diff = sub2(pack2(rp[0], rp[D]), q2);
+        acc[pr] = fma2(diff, diff, acc[pr]);
+      }
+    }
+    float v[8];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) unpack2(acc[pr], v[2 * pr], v[2 * pr + 1]);
+    return warp_tree_sum8(v);
+  }
   if (measure == 0) {
     float v[NW][8];
     if (nrows >= 8) {  // full group: straight-line code, no per-row branches
@@ -238,7 +265,7 @@ struct SpecRow {
   int row;  // lane l: adjacency entry l of `key`
 };
 
-template <class LT, bool FAST, int D32, int NW, bool FILTER>
+template <class LT, bool FAST, int D32, int NW, bool FILTER, bool G4 = false>
 __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
                                       const QueryVec<FAST, D32, NW>& qv, const float* __restrict__ base,
                                       const int* __restrict__ translation, int ck, float xi, Stats& st,
@@ -268,25 +295,39 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
   if (lane < cnt) m = translation ? translation[key_r] : key_r;
 
   float mine = G200_INF;
-  if (FAST && ws.stage_mode == 0 && ws.stage_rows >= 16) {
+  if (FAST && (G4 || ws.stage_mode == 0) && ws.stage_rows >= 16) {
     // software pipeline over 8-row groups: group g lives in buffer g % NBUF with its own mbarrier, so the copies
     // of the next groups are in flight while the distances of the current one are computed
     constexpr int D = 32 * D32;
     const int nbuf = static_cast<int>(ws.stage_rows >> 3);
     const int ngroups = (cnt + 7) >> 3;
+    // gather4: lane l (l % 4 == 0) issues for candidates l .. l+3
     auto issue = [&](int g) {
       const int buf = g % nbuf;
       const int nr = min(8, cnt - 8 * g);
-      if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>(nr) * D * 4u);
-      __syncwarp();
       const int r = lane - 8 * g;
-      if (r >= 0 && r < nr)
-        bulk_g2s(ws.stage + static_cast<size_t>(buf * 8 + r) * D, base + static_cast<size_t>(m) * D, D * 4u, &ws.bar[buf]);
+      if constexpr (G4) {
+        const int mp = lane < cnt ? m : ws.pad_row;
+        const int m1 = __shfl_down_sync(FULL, mp, 1);
+        const int m2 = __shfl_down_sync(FULL, mp, 2);
+        const int m3 = __shfl_down_sync(FULL, mp, 3);
+        if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>((nr + 3) & ~3) * D * 4u);
+        __syncwarp();
+        if (r >= 0 && r < nr && (r & 3) == 0)
+          tma_gather4(ws.stage + static_cast<size_t>(buf * 8 + r) * D, ws.tmap, m, m1, m2, m3, &ws.bar[buf]);
+      }
+      else {
+        if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>(nr) * D * 4u);
+        __syncwarp();
+        if (r >= 0 && r < nr)
+          bulk_g2s(ws.stage + static_cast<size_t>(buf * 8 + r) * D, base + static_cast<size_t>(m) * D, D * 4u, &ws.bar[buf]);
+      }
     };
     for (int g = 0; g < min(nbuf, ngroups); ++g) issue(g);
     for (int g = 0; g < ngroups; ++g) {
       const int buf = g % nbuf;
-      mbar_wait(&ws.bar[buf], (ws.parity >> buf) & 1u);
+      if constexpr (G4) mbar_wait_bounded(&ws.bar[buf], (ws.parity >> buf) & 1u);
+      else mbar_wait(&ws.bar[buf], (ws.parity >> buf) & 1u);
       ws.parity ^= 1u << buf;
       if constexpr (FAST) {
         const float dg = dist8_fast<D32, NW>(ws.stage + static_cast<size_t>(buf) * 8 * D, min(8, cnt - 8 * g), qv.cfg.measure, qv.q, qv.q_norm);
