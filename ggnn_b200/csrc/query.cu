@@ -12,6 +12,10 @@
 #define G200_QUERY_MB 8  // min resident CTAs (4 warps each) per SM the register allocation must allow
 #endif
 
+#ifndef G200_QUERY_MB_G4
+#define G200_QUERY_MB_G4 5  // the gather4 variants keep 16 stage rows per warp: shared memory allows 5 CTAs per SM
+#endif
+
 namespace g200 {
 
 struct QueryArgs {
@@ -32,7 +36,7 @@ struct QueryArgs {
 
 // LT = WarpLists<NS> (best list + prioQ in registers, sorted_size <= 256) or SmemLists (anything larger)
 template <class LT, bool FAST, int NI, bool G4 = false>
-__global__ void __launch_bounds__(128, G200_QUERY_MB) query_kernel(const __grid_constant__ QueryArgs a)
+__global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) query_kernel(const __grid_constant__ QueryArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
@@ -229,16 +233,17 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   rows = std::max(rows, 8u);
   rows = env_u32("GGNN_B200_QUERY_STAGE_ROWS", rows);
   if (rows % 8 || rows == 0 || rows > 32) return set_error(GGNN_B200_ERR_INVALID, "stage rows must be 8, 16, 24 or 32");
-  a.stage_rows = rows;
   // rows must be 16-byte multiples to be staged; default: TMA gather4 (3) where a variant exists, else one bulk copy per row (0)
   a.stage_mode = (p.D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 3);
   if (a.stage_mode == 3) {  // TMA tile::gather4 row staging: register-resident fast kernels with pipelined 8-row groups only
-    if (fast && rows >= 16 && (NI == 3 || NI == 4)) {  // the instantiated gather4 variants
+    if (fast && rows >= 16 && (NI == 3 || NI == 4)) {  // the instantiated gather4 variants (two 8-row buffers)
+      rows = 16;
       if (int rc = make_row_gather_tensor_map(&a.tmap, p.d_base, static_cast<uint64_t>(p.N_base), p.D)) return rc;
       a.pad_row = env_u32("GGNN_B200_GATHER4_PAD_VALID", 0) ? 0 : p.N_base;  // out of bounds: zero fill, no memory traffic
     }
     else a.stage_mode = 0;
   }
+  a.stage_rows = rows;
   a.prefetch = env_u32("GGNN_B200_QUERY_PREFETCH", 2);  // 0 off, 1 L2 prefetch of candidate rows, 2 speculative next-anchor row load
   uint32_t off = align_up(rows * row_bytes, 16);
   a.off_sq = off;

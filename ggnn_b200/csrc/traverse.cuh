@@ -295,39 +295,58 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
   if (lane < cnt) m = translation ? translation[key_r] : key_r;
 
   float mine = G200_INF;
-  if (FAST && (G4 || ws.stage_mode == 0) && ws.stage_rows >= 16) {
+  if constexpr (G4) {
+    // TMA tile::gather4 staging, two 8-row buffers (stage_rows == 16): lane l (l % 4 == 0, l < cnt) fetches candidates
+    // l..l+3 with ONE instruction into rows (l & 15) of the stage; group g = candidates 8g..8g+7 lives in buffer g & 1
+    // and completes on bar[g & 1].  (An mbarrier phase cannot complete before its single arrival, so the order of
+    // expect_tx and the copies does not matter.)
+    constexpr int D = 32 * D32;
+    constexpr uint32_t QUAD_BYTES = 4u * D * 4u;
+    const int ngroups = (cnt + 7) >> 3;
+    const int nquads = (cnt + 3) >> 2;
+    const int mp = lane < cnt ? m : ws.pad_row;
+    const int m1 = __shfl_down_sync(FULL, mp, 1);
+    const int m2 = __shfl_down_sync(FULL, mp, 2);
+    const int m3 = __shfl_down_sync(FULL, mp, 3);
+    const bool issuer = ((lane & 3) == 0) && lane < cnt;
+    float* const dst = ws.stage + (lane & 15) * D;
+    uint64_t* const my_bar = &ws.bar[(lane >> 3) & 1];
+    if (lane == 0) {
+      mbar_expect_tx(&ws.bar[0], static_cast<uint32_t>(min(2, nquads)) * QUAD_BYTES);
+      if (nquads > 2) mbar_expect_tx(&ws.bar[1], static_cast<uint32_t>(min(2, nquads - 2)) * QUAD_BYTES);
+    }
+    if (issuer && lane < 16) tma_gather4(dst, ws.tmap, m, m1, m2, m3, my_bar);
+    for (int g = 0; g < ngroups; ++g) {
+      const int buf = g & 1;
+      mbar_wait(&ws.bar[buf], (ws.parity >> buf) & 1u);
+      ws.parity ^= 1u << buf;
+      const float dg = dist8_fast<D32, NW>(ws.stage + buf * 8 * D, min(8, cnt - 8 * g), qv.cfg.measure, qv.q, qv.q_norm);
+      if ((lane >> 3) == g) mine = dg;
+      __syncwarp();  // the group's rows have been read: its buffer may be refilled
+      if (g + 2 < ngroups) {
+        if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>(min(2, nquads - 2 * (g + 2))) * QUAD_BYTES);
+        if (issuer && (lane >> 3) == g + 2) tma_gather4(dst, ws.tmap, m, m1, m2, m3, my_bar);
+      }
+    }
+  }
+  else if (FAST && ws.stage_mode == 0 && ws.stage_rows >= 16) {
     // software pipeline over 8-row groups: group g lives in buffer g % NBUF with its own mbarrier, so the copies
     // of the next groups are in flight while the distances of the current one are computed
     constexpr int D = 32 * D32;
     const int nbuf = static_cast<int>(ws.stage_rows >> 3);
     const int ngroups = (cnt + 7) >> 3;
-    // gather4: lane l (l % 4 == 0) issues for candidates l .. l+3
     auto issue = [&](int g) {
       const int buf = g % nbuf;
       const int nr = min(8, cnt - 8 * g);
       const int r = lane - 8 * g;
-      if constexpr (G4) {
-        const int mp = lane < cnt ? m : ws.pad_row;
-        const int m1 = __shfl_down_sync(FULL, mp, 1);
-        const int m2 = __shfl_down_sync(FULL, mp, 2);
-        const int m3 = __shfl_down_sync(FULL, mp, 3);
-        if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>((nr + 3) & ~3) * D * 4u);
-        __syncwarp();
-        if (r >= 0 && r < nr && (r & 3) == 0)
-          tma_gather4(ws.stage + static_cast<size_t>(buf * 8 + r) * D, ws.tmap, m, m1, m2, m3, &ws.bar[buf]);
-      }
-      else {
-        if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>(nr) * D * 4u);
-        __syncwarp();
-        if (r >= 0 && r < nr)
-          bulk_g2s(ws.stage + static_cast<size_t>(buf * 8 + r) * D, base + static_cast<size_t>(m) * D, D * 4u, &ws.bar[buf]);
-      }
+      if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>(nr) * D * 4u);
+      if (r >= 0 && r < nr)
+        bulk_g2s(ws.stage + static_cast<size_t>(buf * 8 + r) * D, base + static_cast<size_t>(m) * D, D * 4u, &ws.bar[buf]);
     };
     for (int g = 0; g < min(nbuf, ngroups); ++g) issue(g);
     for (int g = 0; g < ngroups; ++g) {
       const int buf = g % nbuf;
-      if constexpr (G4) mbar_wait_bounded(&ws.bar[buf], (ws.parity >> buf) & 1u);
-      else mbar_wait(&ws.bar[buf], (ws.parity >> buf) & 1u);
+      mbar_wait(&ws.bar[buf], (ws.parity >> buf) & 1u);
       ws.parity ^= 1u << buf;
       if constexpr (FAST) {
         const float dg = dist8_fast<D32, NW>(ws.stage + static_cast<size_t>(buf) * 8 * D, min(8, cnt - 8 * g), qv.cfg.measure, qv.q, qv.q_norm);

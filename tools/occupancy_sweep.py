@@ -24,7 +24,7 @@ def main():
     q4 = query.repeat(4, 1)
     ref = None
     out = []
-    for rows, hs, mode, pad in ((16, 0, 0, 0), (8, 0, 0, 0), (16, 0, 3, 0)):
+    for rows, hs, mode, pad in ((16, 0, 0, 0), (16, 0, 3, 0)):
         os.environ["GGNN_B200_QUERY_STAGE_ROWS"] = str(rows)
         os.environ["GGNN_B200_QUERY_HASH_SLOTS"] = str(hs)
         os.environ["GGNN_B200_STAGE_MODE"] = str(mode)
