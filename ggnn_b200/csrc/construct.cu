@@ -40,7 +40,7 @@ struct WarpPlan {
   uint32_t off_sq, off_half, off_sorted, off_hash, off_ring, off_bar;
 };
 static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uint32_t sorted, uint32_t cache,
-                     uint32_t max_pops, uint32_t target_warps_per_sm)
+                     uint32_t max_pops, uint32_t target_warps_per_sm, uint32_t force_rows = 0)
 {
   const DeviceInfo& dev = device_info();
   const uint32_t row_bytes = D * 4;
@@ -54,6 +54,7 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   rows = std::max(8u, std::min(32u, rows / 8 * 8));
   pl.stage_rows = env_u32("GGNN_B200_BUILD_STAGE_ROWS", rows);
   if (pl.stage_rows % 8 || pl.stage_rows == 0 || pl.stage_rows > 32) pl.stage_rows = rows;
+  if (force_rows && pl.stage_rows >= force_rows) pl.stage_rows = force_rows;
   rows = pl.stage_rows;
   pl.stage_mode = (D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 0);  // rows must be 16-byte multiples to be staged
   if (pl.stage_mode == 3) pl.stage_mode = 0;  // gather4 staging is wired up for the query kernel only
@@ -359,6 +360,8 @@ struct MergeArgs {
   float* nn1;
   uint32_t sorted, cache, max_iterations;
   WarpPlan pl;
+  int32_t pad_row;        // gather4 staging (see traverse.cuh)
+  TensorMapStorage tmap;  // tensor map of the base for the gather4 variants
 };
 
 // simple_knn_cache.cuh:297-333
@@ -404,8 +407,8 @@ __device__ __forceinline__ void lists_transform(WarpLists<NS>& L, const int32_t*
   L.head = BEST;
 }
 
-template <int NS, bool FAST, int D32, int NW>
-__global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
+template <int NS, bool FAST, int D32, int NW, bool G4 = false>
+__global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid_constant__ MergeArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
@@ -415,6 +418,10 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
   WarpSmem ws;
   VisitedSet V;
   init_warp_smem(ws, V, smem_raw + static_cast<size_t>(warp) * a.pl.warp_smem_bytes, a.pl, a.cache - a.sorted);
+  if constexpr (G4) {
+    ws.tmap = &a.tmap;
+    ws.pad_row = a.pad_row;
+  }
 
   const uint32_t K = a.KBuild;
   const float mean_nn1 = a.nn1_stats[0];
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
     const uint32_t s_offset = (seg_btm / powG) * a.S;
     for (uint32_t i = 0; i < a.S; i += 32) {
       const int ck = (i + lane < a.S) ? static_cast<int>(s_offset + i + lane) : EMPTY_KEY;
-      fetch<WarpLists<NS>, FAST, D32, NW, false>(L, V, ws, qv, a.base, a.translation + a.STs_offsets[a.layer_top], ck, xi, st);
+      fetch<WarpLists<NS>, FAST, D32, NW, false, G4>(L, V, ws, qv, a.base, a.translation + a.STs_offsets[a.layer_top], ck, xi, st);
     }
   }
 
@@ -450,7 +457,7 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
     const int32_t* tr = layer ? a.translation + a.STs_offsets[layer] : nullptr;
     if (layer == a.layer_btm) {  // :103-104
       const int ck = lane == 0 ? static_cast<int>(n) : EMPTY_KEY;
-      fetch<WarpLists<NS>, FAST, D32, NW, false>(L, V, ws, qv, a.base, tr, ck, xi, st);
+      fetch<WarpLists<NS>, FAST, D32, NW, false, G4>(L, V, ws, qv, a.base, tr, ck, xi, st);
     }
     const int32_t* layer_graph = a.graph + static_cast<size_t>(a.Ns_offsets[layer]) * K;
     SpecRow spec{EMPTY_KEY, EMPTY_KEY};
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(CW * 32) merge_kernel(const MergeArgs a)
         if (use_spec && spec.key == anchor) ck = spec.row;  // speculative load issued before the previous push loop
         else ck = (j + lane < K) ? __ldg(layer_graph + static_cast<size_t>(anchor) * K + j + lane) : EMPTY_KEY;
         spec.key = EMPTY_KEY;
-        fetch<WarpLists<NS>, FAST, D32, NW, true>(L, V, ws, qv, a.base, tr, ck, xi, st, use_spec ? layer_graph : nullptr, K,
+        fetch<WarpLists<NS>, FAST, D32, NW, true, G4>(L, V, ws, qv, a.base, tr, ck, xi, st, use_spec ? layer_graph : nullptr, K,
                                        use_spec ? &spec : nullptr);
       }
     }
@@ -1071,12 +1078,20 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
   FastSel f = fast_sel(a.D, a.VB, a.items);
   const int NS = a.sorted / 32;
   f.fast = f.fast && f.nw == 1 && NS == 2;  // the register-resident variants that are instantiated
-  if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, 16)) return rc;
+  // gather4 staging (two 8-row buffers) for the register-resident variants with 384/512-byte rows
+  const bool g4 = f.fast && (f.d32 == 3 || f.d32 == 4) && env_u32("GGNN_B200_BUILD_STAGE_MODE", 3) == 3;
+  if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, 16, g4 ? 16 : 0)) return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
   int rc = -1;
 #define G200_MERGE(NS_, FAST_, D32_, NW_) \
   rc = launch_warp_kernel(merge_kernel<NS_, FAST_, D32_, NW_>, a, a.N_btm, smem, stream, "merge_kernel")
-  if (f.fast) {
+  if (g4 && a.pl.stage_rows == 16 && a.pl.stage_mode == 0) {
+    if (int rc2 = make_row_gather_tensor_map(&a.tmap, d_base, cfg->N, cfg->D)) return rc2;
+    a.pad_row = static_cast<int32_t>(cfg->N);  // out of bounds: zero fill, no memory traffic
+    if (f.d32 == 3) rc = launch_warp_kernel(merge_kernel<2, true, 3, 1, true>, a, a.N_btm, smem, stream, "merge_kernel");
+    else rc = launch_warp_kernel(merge_kernel<2, true, 4, 1, true>, a, a.N_btm, smem, stream, "merge_kernel");
+  }
+  else if (f.fast) {
     switch (f.d32) {
       case 1: G200_MERGE(2, true, 1, 1); break;
       case 2: G200_MERGE(2, true, 2, 1); break;
