@@ -188,12 +188,22 @@ def run_ours(a):
     # query batch, so the collectives of batches in flight neither serialise on one communicator nor alias
     n_pipes = max(1, a.streams)
     groups = [dist.new_group(backend="nccl") for _ in range(n_pipes)] if world > 1 else [None] * n_pipes
-    q_bufs = [query if (rank == 0 or world == 1) else torch.empty_like(query) for _ in range(n_pipes)]
+    # Query distribution at N > 1.  "replicated" (default): every rank holds the batch -- device-resident for `value`,
+    # its own pinned host copy for `e2e` (each rank copies host->device over its own PCIe link, exactly what the
+    # reference does: one H2D per GPU, gpu_instance.cu:638-641) -- so the only collective is the top-K exchange.
+    # "broadcast": the batch lives on rank 0 only and is broadcast over NVLink inside the timed region.
+    bcast = world > 1 and a.query_distribution == "broadcast"
+    if world > 1:  # the seeded generator must have produced the same batch everywhere
+        chk = torch.stack((query.double().sum(), query[::97].double().sum()))
+        ref_chk = chk.clone()
+        dist.broadcast(ref_chk, src=0)
+        assert torch.equal(chk, ref_chk), "query batches differ between ranks"
+    q_bufs = [query if (rank == 0 or world == 1 or not bcast) else torch.empty_like(query) for _ in range(n_pipes)]
 
     def step_device(pipe=0):
         if world == 1:
             return local_query(query)
-        return gd.distributed_query(local_query, gd.gpu_merge, q_bufs[pipe], K, a.n_base, group=groups[pipe], broadcast=True)
+        return gd.distributed_query(local_query, gd.gpu_merge, q_bufs[pipe], K, a.n_base, group=groups[pipe], broadcast=bcast)
 
     # ground truth + recall (untimed): exact brute force on every shard, merged the same way
     def bf_local(q):
@@ -279,11 +289,11 @@ def run_ours(a):
     def step_e2e():
         if world == 1:
             return idx.query(q_host, K, a.tau_query, a.max_iterations)   # H2D + kernels + D2H inside
-        qd = q_host.to(dev, non_blocking=True)
+        qd = q_host.to(dev, non_blocking=True) if (rank == 0 or not bcast) else torch.empty_like(query)
         idx.set_return_results_on_gpu(True)
-        r = gd.distributed_query(local_query, gd.gpu_merge, qd, K, a.n_base, broadcast=True)
+        r = gd.distributed_query(local_query, gd.gpu_merge, qd, K, a.n_base, broadcast=bcast)
         return r[0].cpu(), r[1].cpu()
-    for _ in range(max(1, a.warmup // 2)):
+    for _ in range(max(3, a.warmup)):   # (the first calls allocate the pinned result buffers)
         step_e2e()
     if world > 1:
         dist.barrier()
@@ -306,7 +316,7 @@ def run_ours(a):
             while pending:
                 last = pending.pop(0).result()
             return last
-        run_async(max(2, a.warmup // 2))
+        run_async(max(4, a.warmup))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         r_async = run_async(a.steps)
@@ -329,9 +339,9 @@ def run_ours(a):
                 if evs[pipe] is not None:
                     evs[pipe].synchronize()  # the step that used this pipeline's buffers has delivered its result
                 with torch.cuda.stream(streams[pipe]):
-                    if rank == 0:
+                    if rank == 0 or not bcast:
                         qd[pipe].copy_(q_host, non_blocking=True)
-                    r = gd.distributed_query(local_query, gd.gpu_merge, qd[pipe], K, a.n_base, group=groups[pipe], broadcast=True)
+                    r = gd.distributed_query(local_query, gd.gpu_merge, qd[pipe], K, a.n_base, group=groups[pipe], broadcast=bcast)
                     if rank == 0:
                         pin_i[pipe].copy_(r[0], non_blocking=True)
                         pin_d[pipe].copy_(r[1], non_blocking=True)
@@ -339,7 +349,7 @@ def run_ours(a):
             for e in evs:
                 if e is not None:
                     e.synchronize()
-        run_async(max(2, a.warmup // 2))
+        run_async(max(4, a.warmup))
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -378,16 +388,19 @@ def run_ours(a):
                                f"k_query={K} tau_query={a.tau_query} max_iterations={a.max_iterations}",
                    "shards": shards, "vectors_total": a.n_base * shards, "queries_per_s": qps, "recall_at_10": rec,
                    "l2_policy": "inputs_larger_than_l2 (512 MB base per shard, gather-random)",
-                   "parallelism": f"base row-sharded x{shards}, NCCL all_gather of [Nq,K] + merge kernel" if shards > 1 else "single shard",
+                   "parallelism": (f"base row-sharded x{shards}, queries {a.query_distribution}, NCCL all_gather of [Nq,K] + merge kernel"
+                                   if shards > 1 else "single shard"),
                    "build_s": build_s,
                    "pipelining": f"{n_streams} CUDA stream(s): independent query batches overlap their tails" if n_streams > 1
                    else "none (batches serialised on one stream)",
                    "single_batch_ms": kernel_ms},
         "recall_at_10": rec,
         "e2e": {"value": e2e_qps * shards, "unit": "queries/s" if shards == 1 else "queries/s x shards searched",
-                "h2d_bytes_per_step": a.n_query * a.dim * 4, "d2h_bytes_per_step": a.n_query * K * 8,
+                "h2d_bytes_per_step": a.n_query * a.dim * 4 * (1 if (bcast or shards == 1) else shards),
+                "d2h_bytes_per_step": a.n_query * K * 8,
                 "mode": ((f"GGNN.query_async(), {e2e_depth} batches in flight" if shards == 1 else
-                          f"{e2e_depth} batches in flight: pinned H2D on rank 0, broadcast, per-shard query, all_gather, merge, D2H on rank 0")
+                          f"{e2e_depth} batches in flight: " + ("pinned H2D on rank 0, broadcast" if bcast else "pinned H2D on every rank") +
+                          ", per-shard query, all_gather, merge, D2H on rank 0")
                          if e2e_depth > 1 else "one synchronous call per step"),
                 "sync_value": a.n_query / (e2e_sync_ms / a.steps * 1e-3) * shards},
         "gpu_launches": a.steps * (1 + (1 if shards > 1 else 0)),
@@ -530,10 +543,13 @@ def emit(obj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)   # one step = one 10 000-query batch (~0.5 ms)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--query-distribution", dest="query_distribution", default="replicated", choices=["replicated", "broadcast"],
+                    help="N > 1: every rank holds / copies the query batch itself (like the reference's one H2D per GPU), "
+                         "or rank 0 broadcasts it over NVLink inside the timed region")
     ap.add_argument("--e2e-depth", dest="e2e_depth", type=int, default=2,
                     help="batches in flight in the end-to-end measurement (1 = synchronous GGNN.query() per step)")
     for k, v in DEF.items():
