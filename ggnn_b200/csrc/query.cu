@@ -9,7 +9,7 @@
 #include <cstdlib>
 
 #ifndef G200_QUERY_MB
-#define G200_QUERY_MB 8  // min resident CTAs (4 warps each) per SM the register allocation must allow
+#define G200_QUERY_MB 6  // min resident CTAs (4 warps each) per SM the register allocation must allow (80 registers)
 #endif
 
 #ifndef G200_QUERY_MB_G4

@@ -88,6 +88,8 @@ __device__ __forceinline__ float dist8_fast(const float* __restrict__ rows, int 
     for (int pr = 0; pr < 4; ++pr) unpack2(acc[pr], v[2 * pr], v[2 * pr + 1]);
     return warp_tree_sum8(v);
   }
+  // (Cosine stays scalar: the reference's products and sums are separate roundings, and ptxas contracts
+  // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with explicit .rn -- measured, see DESIGN.md -- which changes results.)
   if (measure == 0) {
     float v[NW][8];
     if (nrows >= 8) {  // full group: straight-line code, no per-row branches
