@@ -413,8 +413,6 @@ __global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const uint32_t n = blockIdx.x * CW + warp;
-  if (n >= a.N_btm) return;
   WarpSmem ws;
   VisitedSet V;
   init_warp_smem(ws, V, smem_raw + static_cast<size_t>(warp) * a.pl.warp_smem_bytes, a.pl, a.cache - a.sorted);
@@ -427,6 +425,9 @@ __global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid
   const float mean_nn1 = a.nn1_stats[0];
   const float xi = (a.measure == 0) ? __fmul_rn(__fmul_rn(__fmul_rn(mean_nn1, mean_nn1), a.tau_build), a.tau_build)
                                     : __fmul_rn(mean_nn1, a.tau_build);
+  // persistent warps: warp w of the grid handles points w, w + W, w + 2W, ... -- a warp slot is never held idle by the
+  // slower warps of its CTA, and at any time the resident warps work on one contiguous block of points (L2 locality)
+  for (uint32_t n = blockIdx.x * CW + warp; n < a.N_btm; n += gridDim.x * CW) {
   const int m = a.layer_btm ? a.translation[a.STs_offsets[a.layer_btm] + n] : static_cast<int>(n);
   const DistCfg dc{a.D, a.VB, a.items, a.measure};
   QueryVec<FAST, D32, NW> qv;
@@ -516,6 +517,8 @@ __global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid
     if (a.measure == 0) dist = __fsqrt_rn(dist);
     if (lane == 0) a.nn1[n] = dist;
   }
+  __syncwarp();
+  }  // points of this warp
 }
 
 // ================================================================================================
@@ -926,11 +929,18 @@ static void construction_config(uint32_t D, uint32_t min_block, uint32_t& VB, ui
 }
 
 template <typename Kern, typename Args>
-static int launch_warp_kernel(Kern kern, const Args& a, uint32_t n_items, size_t smem, cudaStream_t stream, const char* what)
+static int launch_warp_kernel(Kern kern, const Args& a, uint32_t n_items, size_t smem, cudaStream_t stream, const char* what,
+                              bool persistent = false)
 {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, what);
-  const uint32_t grid = (n_items + CW - 1) / CW;
+  uint32_t grid = (n_items + CW - 1) / CW;
+  if (persistent && env_u32("GGNN_B200_BUILD_PERSISTENT", 1)) {  // one wave of resident CTAs, each warp loops over its points
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CW * 32, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, what);
+    grid = std::min<uint32_t>(grid, static_cast<uint32_t>(std::max(per_sm, 1)) * device_info().num_sms);
+  }
   kern<<<grid, CW * 32, smem, stream>>>(a);
   return set_cuda_error(cudaGetLastError(), what);
 }
@@ -1084,12 +1094,12 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
   int rc = -1;
 #define G200_MERGE(NS_, FAST_, D32_, NW_) \
-  rc = launch_warp_kernel(merge_kernel<NS_, FAST_, D32_, NW_>, a, a.N_btm, smem, stream, "merge_kernel")
+  rc = launch_warp_kernel(merge_kernel<NS_, FAST_, D32_, NW_>, a, a.N_btm, smem, stream, "merge_kernel", true)
   if (g4 && a.pl.stage_rows == 16 && a.pl.stage_mode == 0) {
     if (int rc2 = make_row_gather_tensor_map(&a.tmap, d_base, cfg->N, cfg->D)) return rc2;
     a.pad_row = static_cast<int32_t>(cfg->N);  // out of bounds: zero fill, no memory traffic
-    if (f.d32 == 3) rc = launch_warp_kernel(merge_kernel<2, true, 3, 1, true>, a, a.N_btm, smem, stream, "merge_kernel");
-    else rc = launch_warp_kernel(merge_kernel<2, true, 4, 1, true>, a, a.N_btm, smem, stream, "merge_kernel");
+    if (f.d32 == 3) rc = launch_warp_kernel(merge_kernel<2, true, 3, 1, true>, a, a.N_btm, smem, stream, "merge_kernel", true);
+    else rc = launch_warp_kernel(merge_kernel<2, true, 4, 1, true>, a, a.N_btm, smem, stream, "merge_kernel", true);
   }
   else if (f.fast) {
     switch (f.d32) {

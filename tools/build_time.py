@@ -12,8 +12,9 @@ import ggnn_b200 as ggnn  # noqa: E402
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "manifold8"
 base, query = bench.gen_gpu(1_000_000, 10_000, 128, kind, 1234, torch.device("cuda", 0))
-for mode in ("0", "3", "0", "3"):
+for mode, pers in (("3", "0"), ("3", "1"), ("0", "1"), ("3", "0"), ("3", "1")):
     os.environ["GGNN_B200_BUILD_STAGE_MODE"] = mode
+    os.environ["GGNN_B200_BUILD_PERSISTENT"] = pers
     idx = ggnn.GGNN()
     idx.set_return_results_on_gpu(True)
     idx.set_base(base)
@@ -25,5 +26,5 @@ for mode in ("0", "3", "0", "3"):
     ids, _ = idx.query(query, 10, 0.64, 400)
     gt, _ = idx.bf_query(query, 10)
     rec = ggnn.Evaluator(None, None, gt.cpu(), 10).evaluate_results(ids.cpu()).c_k_query
-    print(f"build stage mode {mode}: {dt:.3f} s, recall@10 {rec:.4f}", flush=True)
+    print(f"build stage mode {mode} persistent {pers}: {dt:.3f} s, recall@10 {rec:.4f}", flush=True)
     del idx
