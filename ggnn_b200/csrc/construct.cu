@@ -536,6 +536,8 @@ struct SymArgs {
   uint32_t* sym_atomic;
   uint32_t sorted, cache, max_iterations;
   WarpPlan pl;
+  int32_t pad_row;        // gather4 staging (see traverse.cuh); stage_mode 3 in `pl` switches it on
+  TensorMapStorage tmap;
 };
 
 // two distances (to the point itself and to the half-way point) of up to 8 staged rows, in the
@@ -548,6 +550,41 @@ __device__ __forceinline__ void sym_dist8(const float* __restrict__ rows, int nr
   const int lane = lane_id();
   constexpr int D = 32 * D32;
   float tq = 0.f, th = 0.f, tn = 0.f;
+  if (measure == 0 && G200_PACKED_DIST) {
+    // Euclidean: rows (2p, 2p+1) advance together in packed fp32 (sub.rn + fma.rn per element, like the scalar chain);
+    // always the whole group -- rows >= nrows hold stale shared memory, their results are never used
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      uint64_t aq[4] = {0ull, 0ull, 0ull, 0ull}, ah[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int c = it * NW + w;
+        if (c < D32) {
+          const uint64_t q2 = pack2(q[c], q[c]), h2 = pack2(h[c], h[c]);
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            const float* rp = rows + (2 * pr) * D + 32 * c + lane;
+            const uint64_t o2 = pack2(rp[0], rp[D]);
+            const uint64_t dq = sub2(q2, o2), dh = sub2(h2, o2);
+            aq[pr] = fma2(dq, dq, aq[pr]);
+            ah[pr] = fma2(dh, dh, ah[pr]);
+          }
+        }
+      }
+      float vq[8], vh[8];
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        unpack2(aq[pr], vq[2 * pr], vq[2 * pr + 1]);
+        unpack2(ah[pr], vh[2 * pr], vh[2 * pr + 1]);
+      }
+      const float sq = warp_tree_sum8(vq), sh = warp_tree_sum8(vh);
+      tq = (w == 0) ? sq : tq + sq;
+      th = (w == 0) ? sh : th + sh;
+    }
+    out_q = tq;
+    out_h = th;
+    return;
+  }
 #pragma unroll
   for (int w = 0; w < NW; ++w) {
     float vq[8], vh[8], vn[8];
@@ -696,7 +733,7 @@ __device__ __forceinline__ void sym_stage_and_dist(WarpSmem& ws, const SymVec<FA
 }
 
 template <int NS, bool FAST, int D32, int NW>
-__global__ void __launch_bounds__(CW * 32) sym_kernel(const SymArgs a)
+__global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ SymArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
@@ -707,6 +744,10 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const SymArgs a)
   WarpSmem ws;
   VisitedSet V;
   init_warp_smem(ws, V, wbase, a.pl, a.cache - a.sorted);
+  if (a.pl.stage_mode == 3) {
+    ws.tmap = &a.tmap;
+    ws.pad_row = a.pad_row;
+  }
 
   const uint32_t K = a.KBuild, KF = K / 2, KL = K - KF;
   const float mean_nn1 = a.nn1_stats[0];
@@ -1164,6 +1205,11 @@ extern "C" int ggnn_b200_sym(const ggnn_b200_graph_config* cfg, const float* d_b
   const int NS = a.sorted / 32;
   f.fast = f.fast && f.nw == 2 && NS == 2;
   if (int rc = make_plan(a.pl, a.D, !f.fast, !f.fast, a.sorted, a.cache, a.max_iterations, 16)) return rc;
+  if (f.fast && a.pl.stage_mode == 0 && a.D <= 256 && env_u32("GGNN_B200_BUILD_STAGE_MODE", 3) == 3) {
+    if (int rc = make_row_gather_tensor_map(&a.tmap, d_base, cfg->N, cfg->D)) return rc;
+    a.pad_row = static_cast<int32_t>(cfg->N);  // out of bounds: zero fill, no memory traffic
+    a.pl.stage_mode = 3;
+  }
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
 #define G200_SYM(NS_, FAST_, D32_, NW_) \
   return launch_warp_kernel(sym_kernel<NS_, FAST_, D32_, NW_>, a, a.N_layer, smem, stream, "sym_kernel")

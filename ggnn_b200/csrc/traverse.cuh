@@ -33,7 +33,18 @@ __device__ __forceinline__ void stage_rows_g2s(WarpSmem& ws, const float* __rest
 {
   const int lane = lane_id();
   const uint32_t row_bytes = D * 4u;
-  if (ws.stage_mode == 0 || ws.stage_mode == 3) {
+  if (ws.stage_mode == 3 && ws.tmap) {  // TMA tile::gather4: lane b0 + 4j fetches rows b0+4j .. b0+4j+3 with one instruction
+    const int r = lane - b0;
+    const int mp = (r >= 0 && r < nb) ? m : ws.pad_row;
+    const int m1 = __shfl_down_sync(FULL, mp, 1);
+    const int m2 = __shfl_down_sync(FULL, mp, 2);
+    const int m3 = __shfl_down_sync(FULL, mp, 3);
+    if (lane == 0) mbar_expect_tx(ws.bar, row_bytes * static_cast<uint32_t>((nb + 3) & ~3));
+    if (r >= 0 && r < nb && (r & 3) == 0) tma_gather4(ws.stage + static_cast<size_t>(r) * D, ws.tmap, mp, m1, m2, m3, ws.bar);
+    mbar_wait(ws.bar, ws.parity & 1u);
+    ws.parity ^= 1u;
+  }
+  else if (ws.stage_mode == 0 || ws.stage_mode == 3) {
     if (lane == 0) mbar_expect_tx(ws.bar, row_bytes * nb);
     __syncwarp();
     const int r = lane - b0;
