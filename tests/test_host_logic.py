@@ -146,3 +146,77 @@ def test_oracle_merge_semantics():
     oi, od = O.merge_results(ids, d, 3, 1000)
     assert od.tolist() == [[np.float32(0.1), np.float32(0.2), np.float32(0.4)]]
     assert oi.tolist() == [[0, 1000, 1]]  # tie 0.4: lower partition first; ids re-based (result_merger.cpp:115-116)
+
+
+# ------------------------------------------------------------------------------------------------
+# The device keeps the best list + prioQ ring in registers (WarpLists) or shared memory (SmemLists) and updates ALL
+# slots of a push at once (ggnn_b200/csrc/common.cuh); the reference walks the list block by block from the top
+# (simple_knn_cache.cuh:160-211).  The model below is the device's update rule written in numpy; it must leave
+# exactly the state of the oracle's lock-step emulation of the reference -- for every block width, ring position
+# (wrapped or not: the ring-wrap quirk of SURVEY appendix A included) and list size, also the ones beyond one warp.
+# ------------------------------------------------------------------------------------------------
+class _SlotParallelLists:
+    EMPTY = -1
+
+    def __init__(self, best, sorted_size):
+        self.best, self.sorted = best, sorted_size
+        self.key = np.full(sorted_size, self.EMPTY, np.int32)
+        self.dist = np.full(sorted_size, np.inf, np.float32)
+        self.head = best
+
+    def push(self, k, d):
+        d = np.float32(d)
+        if (self.key == k).any():
+            return
+        p = np.arange(self.sorted)
+        pk = np.roll(self.key, 1)
+        pd = np.roll(self.dist, 1)
+        recv = (p >= 1) & (p != self.best) & (p != self.head) & (pd >= d) & (pk != self.EMPTY)
+        asd = np.where(recv, pd, self.dist)
+        nk = np.where(recv, pk, self.key)
+        pa = np.roll(asd, 1)
+        pa[self.best] = asd[self.sorted - 1]
+        active = self.dist >= d
+        has_prev = (p != 0) & (p != self.head)
+        ins = active & (~has_prev | (pa < d))
+        self.key = np.where(ins, np.int32(k), nk).astype(np.int32)
+        self.dist = np.where(ins, d, asd).astype(np.float32)
+
+    def pop(self, criteria):
+        k, dd = int(self.key[self.head]), self.dist[self.head]
+        if k == self.EMPTY or dd >= criteria:
+            return self.EMPTY
+        self.key[self.head], self.dist[self.head] = self.EMPTY, np.inf
+        self.head = self.best if self.head + 1 >= self.sorted else self.head + 1
+        return k
+
+
+@pytest.mark.parametrize("best,sorted_size,cache,vblock", [
+    (10, 32, 512, 32), (10, 64, 256, 32), (25, 64, 256, 32), (100, 128, 512, 32), (10, 32, 1024, 64),
+    (150, 192, 512, 32), (239, 256, 512, 32), (300, 320, 512, 32), (1000, 1024, 2048, 128), (40, 64, 512, 256)])
+def test_slot_parallel_list_update_equals_reference_block_loop(best, sorted_size, cache, vblock):
+    rng = np.random.default_rng(best * 7 + sorted_size)
+    ref = O.Cache(best, sorted_size, cache, vblock, xi=0.25)
+    dev = _SlotParallelLists(best, sorted_size)
+    n_ops = 6 * sorted_size
+    next_key = 0
+    for step in range(n_ops):
+        if rng.random() < 0.3 and step > sorted_size // 2:
+            # pop: criteria() = dist[BEST-1] + xi (simple_knn_cache.cuh:121-124, 223)
+            _, dists, _, _ = ref.state()
+            want = ref.pop()
+            got = dev.pop(np.float32(dists[best - 1] + np.float32(0.25)))
+            assert got == want, step
+        else:
+            if rng.random() < 0.1 and next_key > 0:
+                key = int(rng.integers(0, next_key))       # a key that may already be cached (dedupe, :132-146)
+            else:
+                key, next_key = next_key, next_key + 1
+            # distances from a small grid -> many exact ties (the shift / insert rules differ on >= vs <)
+            d = np.float32(rng.integers(0, 4 * sorted_size) / 8.0)
+            ref.push(key, d)
+            dev.push(key, d)
+        keys, dists, ph, _ = ref.state()
+        assert ph == dev.head, step
+        assert np.array_equal(keys[:sorted_size], dev.key), step
+        assert np.array_equal(dists, dev.dist), step
