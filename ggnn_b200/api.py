@@ -17,7 +17,7 @@ from enum import IntEnum
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, swap
 
 
 class DistanceMeasure(IntEnum):  # include/ggnn/base/def.h:27-30
@@ -85,11 +85,13 @@ class Graph:
 
 
 class _Shard:
-    def __init__(self, device, base, global_id):
+    def __init__(self, device, base, global_id, pool=None, host_rows=None):
         self.device = device
-        self.base = base          # [N_shard, D] fp32 on `device`
+        self.base = base          # [N_shard, D] fp32 on `device` (None in swap mode: see ggnn_b200/swap.py)
         self.global_id = global_id
-        self.graph = None         # Graph
+        self.graph = None         # Graph (resident mode)
+        self.pool = pool          # swap.ShardPool of this shard's GPU, or None = everything stays resident
+        self.host_rows = host_rows  # swap mode: view of the host base tensor
 
 
 class QueryFuture:
@@ -126,15 +128,20 @@ class GGNN:
         self._base_dtype = torch.float32
         self._host_streams = {}
         self._host_rr = 0
+        self._pools = []          # per GPU: swap.ShardPool or None (all shards resident)
+        self._query_calls = 0
 
     # ---- configuration (ggnn.cu:53-60, 420-454) ----
     def set_working_directory(self, path):
         self._workdir = str(path)
 
     def set_cpu_memory_limit(self, limit):
-        self._cpu_limit = int(limit)  # shards stay resident in HBM here (180 GB per GPU)
+        # pinned host memory the swapped-out graphs may use; beyond it they go to part_<id>.ggnn files in the working
+        # directory (gpu_instance.cu:177-200).  Irrelevant while all shards of a GPU fit into its memory.
+        self._cpu_limit = int(limit)
 
     def set_reserved_gpu_memory(self, reserved):
+        # GPU memory to leave free for queries / results when counting how many shards fit (gpu_instance.cu:150-175)
         self._reserved = int(reserved)
 
     def set_gpus(self, gpu_ids):
@@ -189,13 +196,32 @@ class GGNN:
         self._spg = num_shards // len(self._gpus)
         self._n_shard = n_shard
         self._kbuild = k_build
+        l = _lib.lib()  # fail early if the CUDA library is missing
+        cfg = self._cfg()
+        blob_bytes = l.ggnn_b200_graph_blob_bytes(C.byref(cfg))
+        shard_bytes = n_shard * self._base.shape[1] * 4 + blob_bytes
+        scratch_bytes = l.ggnn_b200_build_scratch_bytes(C.byref(cfg))
         for gi, gpu in enumerate(self._gpus):
             dev = torch.device("cuda", gpu)
+            # how many shards fit on this GPU (gpu_instance.cu:135-227); a base that already lives on the GPU stays there
+            n_buf = self._spg
+            if not self._base.is_cuda:
+                free_bytes, _ = torch.cuda.mem_get_info(dev)
+                n_buf = swap.plan_gpu_buffers(free_bytes, getattr(self, "_reserved", 0), scratch_bytes, shard_bytes, self._spg,
+                                              int(os.environ.get("GGNN_B200_GPU_SHARD_BUFFERS", "0")))
+            pool = None
+            if n_buf < self._spg:
+                n_cpu = swap.plan_cpu_buffers(getattr(self, "_cpu_limit", None), blob_bytes, self._spg)
+                pool = swap.ShardPool(dev, n_buf, n_shard, self._base.shape[1], blob_bytes, n_cpu, self._workdir)
+                _log(1, f"GPU {gpu}: {n_buf} of {self._spg} shards resident, {n_cpu} graphs in pinned host memory, rest on disk")
+            self._pools.append(pool)
             for s in range(self._spg):
                 gid = gi * self._spg + s
                 rows = self._base[gid * n_shard:(gid + 1) * n_shard]
-                self._shards.append(_Shard(dev, rows.to(dev, non_blocking=True).contiguous(), gid))
-        _lib.lib()  # fail early if the CUDA library is missing
+                if pool is None:
+                    self._shards.append(_Shard(dev, rows.to(dev, non_blocking=True).contiguous(), gid))
+                else:
+                    self._shards.append(_Shard(dev, None, gid, pool, rows))
 
     def _cfg(self):
         return _lib.graph_config(self._n_shard, self._base.shape[1], self._kbuild)
@@ -207,24 +233,42 @@ class GGNN:
         l = _lib.lib()
         blob_bytes = l.ggnn_b200_graph_blob_bytes(C.byref(cfg))
         scratch_bytes = l.ggnn_b200_build_scratch_bytes(C.byref(cfg))
-        for sh in self._shards:
+        for i, sh in enumerate(self._shards):
             with torch.cuda.device(sh.device):
-                blob = torch.zeros(blob_bytes, dtype=torch.uint8, device=sh.device)
+                if sh.pool is None:
+                    base, blob = sh.base, torch.zeros(blob_bytes, dtype=torch.uint8, device=sh.device)
+                else:  # swap mode: build in a pool slot, start loading the next shard of this GPU meanwhile
+                    base, blob = sh.pool.acquire(sh.global_id, sh.host_rows)
+                    blob.zero_()
+                    nxt = self._shards[i + 1] if i + 1 < len(self._shards) else None
+                    if nxt is not None and nxt.pool is sh.pool:
+                        sh.pool.prefetch(nxt.global_id, nxt.host_rows, keep=(sh.global_id,))
                 scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=sh.device)
-                _lib.check(l.ggnn_b200_build_graph(C.byref(cfg), _ptr(sh.base), int(measure), float(tau_build),
+                _lib.check(l.ggnn_b200_build_graph(C.byref(cfg), _ptr(base), int(measure), float(tau_build),
                                                    int(refinement_iterations), None, _ptr(blob), _ptr(scratch),
                                                    scratch_bytes, _stream_ptr(sh.device)))
-                sh.graph = Graph(cfg, blob)
+                if sh.pool is None:
+                    sh.graph = Graph(cfg, blob)
+                else:
+                    sh.pool.mark_built(sh.global_id)
                 torch.cuda.current_stream(sh.device).synchronize()
                 del scratch
         self._measure = int(measure)
 
+    def _has_graph(self):
+        return bool(self._shards) and all((sh.graph is not None) if sh.pool is None else (sh.global_id in sh.pool.has_graph)
+                                          for sh in self._shards)
+
     def store(self):
-        if not self._shards or self._shards[0].graph is None:
+        if not self._has_graph():
             raise RuntimeError("There is no graph to store.")
         os.makedirs(self._workdir, exist_ok=True)
         for sh in self._shards:  # gpu_instance.cu:86-115: part_<global_shard_id>.ggnn = raw blob
-            sh.graph.blob.cpu().numpy().tofile(os.path.join(self._workdir, f"part_{sh.global_id}.ggnn"))
+            path = os.path.join(self._workdir, f"part_{sh.global_id}.ggnn")
+            if sh.pool is None:
+                sh.graph.blob.cpu().numpy().tofile(path)
+            else:
+                sh.pool.blob_to_file(sh.global_id, path)
 
     def load(self, k_build):
         self._prepare(int(k_build))
@@ -234,11 +278,25 @@ class GGNN:
             path = os.path.join(self._workdir, f"part_{sh.global_id}.ggnn")
             if os.path.getsize(path) != nbytes:  # gpu_instance.cu:454-455 validates by size only
                 raise RuntimeError(f"{path}: unexpected file size")
+            if sh.pool is not None:
+                sh.pool.adopt_file(sh.global_id)   # read when the shard is swapped in
+                continue
             blob = torch.from_numpy(np.fromfile(path, dtype=np.uint8)).to(sh.device)
             sh.graph = Graph(cfg, blob)
 
+    def _resident(self, sh, keep=()):
+        """-> (base rows, Graph) of a shard on its device; swap mode: valid until the shard is evicted"""
+        if sh.pool is None:
+            return sh.base, sh.graph
+        base, blob = sh.pool.acquire(sh.global_id, sh.host_rows, keep)
+        return base, Graph(self._cfg(), blob)
+
     def get_graph(self, global_shard_id=0):
-        return self._shards[global_shard_id].graph
+        sh = self._shards[global_shard_id]
+        if sh.pool is None:
+            return sh.graph
+        with torch.cuda.device(sh.device):
+            return self._resident(sh)[1]
 
     # ---- query ----
     def _counter(self, device):
@@ -257,16 +315,28 @@ class GGNN:
         with torch.cuda.device(dev):
             ids = torch.empty((Nq, k_query * self._spg), dtype=torch.int32, device=dev)
             dists = torch.empty((Nq, k_query * self._spg), dtype=torch.float32, device=dev)
-            for s, sh in enumerate(shards):
-                cfg = sh.graph.config
+            order = list(range(len(shards)))
+            if shards[0].pool is not None:
+                # swap mode: alternate the direction from call to call, so that the shards left on the GPU by the
+                # previous call are searched first (gpu_instance.cu:669-670, 740)
+                if self._query_calls % 2:
+                    order.reverse()
+                self._query_calls += 1
+            for oi, s in enumerate(order):
+                sh = shards[s]
+                sh_base, sh_graph = self._resident(sh)
+                if sh.pool is not None and oi + 1 < len(order):
+                    nxt = shards[order[oi + 1]]
+                    sh.pool.prefetch(nxt.global_id, nxt.host_rows, keep=(sh.global_id,))
+                cfg = sh_graph.config
                 p = _lib.QueryParams()
                 p.D, p.measure, p.KQuery = cfg.D, int(measure), int(k_query)
                 p.tau_query, p.max_iterations = float(tau_query), int(max_iterations)
                 p.N_base, p.KBuild, p.num_starting_points = cfg.N, cfg.KBuild, cfg.S
-                p.d_base, p.d_query = sh.base.data_ptr(), q_dev.data_ptr()
-                p.d_graph = sh.graph.graph.data_ptr()
-                p.d_starting_points = sh.graph.layer_translation(_lib.L - 1).data_ptr()
-                p.d_nn1_stats = sh.graph.nn1_stats.data_ptr()
+                p.d_base, p.d_query = sh_base.data_ptr(), q_dev.data_ptr()
+                p.d_graph = sh_graph.graph.data_ptr()
+                p.d_starting_points = sh_graph.layer_translation(_lib.L - 1).data_ptr()
+                p.d_nn1_stats = sh_graph.nn1_stats.data_ptr()
                 p.d_query_results, p.d_query_results_dists = ids.data_ptr(), dists.data_ptr()
                 p.shards_per_gpu, p.on_gpu_shard_id = self._spg, s
                 p.d_work_counter = self._counter(dev).data_ptr()
@@ -280,7 +350,7 @@ class GGNN:
         return ids, dists
 
     def query(self, query, k_query, tau_query, max_iterations=400, measure=DistanceMeasure.Euclidean):
-        if not self._shards or self._shards[0].graph is None:
+        if not self._has_graph():
             raise RuntimeError("There is no graph to query.")
         query = _as_tensor(query, "query")
         if query.dtype != getattr(self, "_base_dtype", torch.float32):
@@ -329,7 +399,7 @@ class GGNN:
         returned QueryFuture waits for them and hands out (ids, dists) in pinned host memory.  Several batches may be
         in flight at once: their copies overlap the other batches' kernels, and the SMs a batch's last long queries
         leave idle are filled by the next batch.  (The reference's query is synchronous only: ggnn.cu:506-551.)"""
-        if not self._shards or self._shards[0].graph is None:
+        if not self._has_graph():
             raise RuntimeError("There is no graph to query.")
         query = _as_tensor(query, "query")
         if query.dtype != getattr(self, "_base_dtype", torch.float32):
@@ -385,7 +455,7 @@ class GGNN:
         dev = torch.device("cuda", self._gpus[0])
         l = _lib.lib()
         with torch.cuda.device(dev):
-            if self._shards and len(self._shards) == 1:
+            if self._shards and len(self._shards) == 1 and self._shards[0].pool is None:
                 base = self._shards[0].base
             else:
                 base = self._base.to(dev).contiguous()

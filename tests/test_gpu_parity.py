@@ -559,6 +559,53 @@ def test_reference_benchmark_program_runs_on_our_library(tmp_path, ext):
     assert np.array_equal(ids.cpu().numpy(), gt)
 
 
+def test_shard_swapping_gives_the_resident_results(tmp_path, monkeypatch):
+    """4 shards on one GPU with only 2 (then 1) shard buffers: shards swapped GPU <-> pinned RAM <-> part files
+    (ggnn_b200/swap.py; reference gpu_instance.cu:370-467) must give exactly the results of the all-resident run on
+    the same graphs (construction itself is not deterministic, so the graphs travel through store() / load())"""
+    import os
+    N, D, n_shard, K = 40000, 64, 10000, 10
+    base, query = gen_data(N, 300, D, seed=5)
+    b, q = torch.from_numpy(base), torch.from_numpy(query)
+    blob_bytes = _lib.lib().ggnn_b200_graph_blob_bytes(C.byref(_lib.graph_config(n_shard, D, 24)))
+
+    def make(buffers, cpu_limit, workdir):
+        monkeypatch.setenv("GGNN_B200_GPU_SHARD_BUFFERS", str(buffers))
+        g = ggnn.GGNN()
+        g.set_working_directory(workdir)
+        g.set_shard_size(n_shard)
+        if cpu_limit is not None:
+            g.set_cpu_memory_limit(cpu_limit)
+        g.set_base(b)
+        return g
+
+    wd = os.path.join(tmp_path, "graphs")
+    a = make(2, blob_bytes + 1, wd)               # 2 GPU buffers, 1 graph in pinned RAM, 2 on disk
+    a.build(24, 0.5)
+    pool = a._pools[0]
+    assert pool is not None and len(pool.slots) == 2 and pool.stats["evictions"] >= 2 and pool.on_disk
+    r1 = a.query(q, K, 0.64, 400)
+    r2 = a.query(q, K, 0.64, 400)                 # the second call walks the shards in the opposite direction
+    assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1])
+    gt, _ = a.bf_query(q, K)
+    assert ggnn.Evaluator(base, query, gt, K).evaluate_results(r1[0]).c_k_query > 0.9
+    a.store()
+    assert all(os.path.getsize(os.path.join(wd, f"part_{i}.ggnn")) == blob_bytes for i in range(4))
+
+    r = make(0, None, wd)                         # everything resident (the default on a B200)
+    r.load(24)
+    assert r._pools[0] is None
+    rr = r.query(q, K, 0.64, 400)
+    assert torch.equal(rr[0], r1[0]) and torch.equal(rr[1], r1[1])
+
+    c = make(1, 0, wd)                            # one GPU buffer, nothing in host memory: every shard comes from disk
+    c.load(24)
+    rc = c.query(q, K, 0.64, 400)
+    assert torch.equal(rc[0], r1[0]) and torch.equal(rc[1], r1[1])
+    assert c._pools[0].stats["disk_reads"] >= 4
+    assert torch.equal(c.get_graph(2).graph.cpu(), r.get_graph(2).graph.cpu())
+
+
 def test_uint8_base_vectors_match_oracle_on_widened_values():
     """BaseT = uint8_t (lib.h:26-28): the reference computes on static_cast<float>(value), so results must equal the
     fp32 path / oracle on the widened vectors; query dtype must match the base dtype (ggnn.cu:524-540)"""

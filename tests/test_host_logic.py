@@ -220,3 +220,62 @@ def test_slot_parallel_list_update_equals_reference_block_loop(best, sorted_size
         assert ph == dev.head, step
         assert np.array_equal(keys[:sorted_size], dev.key), step
         assert np.array_equal(dists, dev.dist), step
+
+
+# ------------------------------------------------------------------------------------------------
+# shard swapping GPU <-> pinned RAM <-> disk (ggnn_b200/swap.py; reference: gpu_instance.cu:135-227, 370-467)
+# ------------------------------------------------------------------------------------------------
+def test_swap_planning_rules():
+    from ggnn_b200 import swap
+    GB = 1 << 30
+    assert swap.plan_gpu_buffers(180 * GB, 1 * GB, 2 * GB, 8 * GB, 8) == 8          # everything fits: resident
+    assert swap.plan_gpu_buffers(40 * GB, 1 * GB, 2 * GB, 8 * GB, 8) == 4           # (40-1-2)/8
+    assert swap.plan_gpu_buffers(40 * GB, 30 * GB, 2 * GB, 8 * GB, 8) == 1
+    with pytest.raises(RuntimeError):
+        swap.plan_gpu_buffers(8 * GB, 1 * GB, 2 * GB, 8 * GB, 8)                     # not even one shard
+    assert swap.plan_gpu_buffers(1, 0, 0, 8 * GB, 8, override=3) == 3
+    assert swap.plan_cpu_buffers(None, GB, 5) == 5
+    assert swap.plan_cpu_buffers(int(2.5 * GB), GB, 5) == 2
+    assert swap.plan_cpu_buffers(0, GB, 5) == 0
+
+
+def test_shard_pool_lru_writeback_and_disk(tmp_path):
+    """the pool on the CPU device (same code path minus streams): least-recently-used replacement, dirty graphs are
+    written back to host memory first and to part files beyond the CPU budget, files can be adopted and stored"""
+    from ggnn_b200 import swap
+    rows, dim, blob_bytes = 4, 3, 64
+    host = torch.arange(5 * rows * dim, dtype=torch.float32).view(5 * rows, dim)
+    pool = swap.ShardPool("cpu", 2, rows, dim, blob_bytes, n_cpu=1, workdir=str(tmp_path))
+
+    def rows_of(g):
+        return host[g * rows:(g + 1) * rows]
+
+    # "build" shards 0..4 through two slots
+    for g in range(5):
+        base, blob = pool.acquire(g, rows_of(g))
+        assert torch.equal(base, rows_of(g)) and int(blob.sum()) == 0      # base rows loaded, empty graph
+        blob.fill_(g + 1)
+        pool.mark_built(g)
+    assert list(pool.resident) == [3, 4] and pool.stats["evictions"] == 3
+    assert set(pool.host_blob) == {0} and pool.on_disk == {1, 2}           # one graph fits the CPU budget, the rest on disk
+    assert os.path.getsize(os.path.join(tmp_path, "part_1.ggnn")) == blob_bytes
+    # reading them back in reverse order (the query loop alternates its direction): 4 and 3 are still resident
+    for g in (4, 3, 2, 1, 0):
+        base, blob = pool.acquire(g, rows_of(g), keep=())
+        assert torch.equal(base, rows_of(g)) and bool((blob == g + 1).all()), g
+    assert pool.stats["disk_reads"] == 2 and pool.stats["loads"] == 5 + 3
+    assert pool.on_disk == {1, 2, 3, 4}                                    # 3 and 4 were dirty when evicted
+    # prefetch never evicts the shard being worked on
+    pool.acquire(0, rows_of(0))
+    pool.prefetch(2, rows_of(2), keep=(0,))
+    assert 0 in pool.resident and 2 in pool.resident
+    # store: newest copy wins; adopt: an existing file replaces whatever is cached
+    out = os.path.join(tmp_path, "out.ggnn")
+    pool.blob_to_file(0, out)
+    assert np.fromfile(out, dtype=np.uint8).tolist() == [1] * blob_bytes
+    np.full(blob_bytes, 9, np.uint8).tofile(os.path.join(tmp_path, "part_0.ggnn"))
+    pool.adopt_file(0)
+    _, blob = pool.acquire(0, rows_of(0))
+    assert bool((blob == 9).all())
+    with pytest.raises(RuntimeError):
+        swap.ShardPool("cpu", 1, rows, dim, blob_bytes, 0, str(tmp_path)).blob_to_file(7, out)
