@@ -60,23 +60,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
   }
 }
-// same, but traps instead of spinning forever (used by the tensor-map staging mode: a malformed descriptor would
-// otherwise never complete the transaction count)
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity)
-{
-  uint32_t ok = 0;
-  const uint32_t a = smem_u32(bar);
-  for (uint32_t spins = 0; !ok; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (spins > (1u << 24)) __trap();
-  }
-}
 // one row: global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
