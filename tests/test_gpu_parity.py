@@ -559,6 +559,31 @@ def test_reference_benchmark_program_runs_on_our_library(tmp_path, ext):
     assert np.array_equal(ids.cpu().numpy(), gt)
 
 
+def test_python_benchmark_cli_runs(tmp_path, capsys):
+    """tools/ggnn_benchmark.py (the reference's benchmark procedure on the Python API): builds, exports the ground
+    truth, stores the graph; a second run loads both and reports the same recall"""
+    import os
+    import re
+    from tests.test_host_logic import _write_vecs
+    from tools import ggnn_benchmark as B
+    rng = np.random.default_rng(12)
+    N, Nq, D = 12000, 300, 64
+    latent = rng.standard_normal((N + Nq, 8)).astype(np.float32) @ rng.standard_normal((8, D)).astype(np.float32)
+    data = np.clip(np.rint(latent * 12 + 128 + rng.standard_normal((N + Nq, D))), 0, 255).astype(np.uint8)
+    bp, qp, gp, gd = (os.path.join(tmp_path, f) for f in ("base.bvecs", "query.bvecs", "gt.ivecs", "graphs"))
+    _write_vecs(bp, data[:N])
+    _write_vecs(qp, data[N:])
+    os.makedirs(gd)
+    argv = ["--base", bp, "--query", qp, "--gt", gp, "--graph_dir", gd, "--max_iterations", "400"]
+    runs = []
+    for _ in range(2):
+        B.main(argv)
+        out = capsys.readouterr().out
+        runs.append([float(x) for x in re.findall(r"c@10: ([0-9.]+)", out)])
+    assert len(runs[0]) == 4 and runs[0] == runs[1] and runs[0][-1] > 0.95
+    assert os.path.exists(os.path.join(gd, "part_0.ggnn")) and os.path.getsize(gp) == Nq * 101 * 4
+
+
 def test_shard_swapping_gives_the_resident_results(tmp_path, monkeypatch):
     """4 shards on one GPU with only 2 (then 1) shard buffers: shards swapped GPU <-> pinned RAM <-> part files
     (ggnn_b200/swap.py; reference gpu_instance.cu:370-467) must give exactly the results of the all-resident run on

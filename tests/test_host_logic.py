@@ -279,3 +279,19 @@ def test_shard_pool_lru_writeback_and_disk(tmp_path):
     assert bool((blob == 9).all())
     with pytest.raises(RuntimeError):
         swap.ShardPool("cpu", 1, rows, dim, blob_bytes, 0, str(tmp_path)).blob_to_file(7, out)
+
+
+def test_benchmark_cli_mirrors_the_reference_flags():
+    """tools/ggnn_benchmark.py: flag names / defaults of examples/cpp-and-cuda/ggnn_benchmark.cpp:37-50 and its tau lists"""
+    from tools import ggnn_benchmark as B
+    a = B.parse_args(["--base", "b.fvecs", "--query", "q.fvecs"])
+    assert (a.k_build, a.tau_build, a.refinement_iterations, a.k_query, a.max_iterations) == (24, 0.5, 2, 10, 200)
+    assert (a.measure, a.shard_size, a.gpus, a.grid_search, a.subset, a.gt, a.graph_dir) == ("euclidean", 0, [0], False, 0, "", "")
+    a = B.parse_args(["--base", "b.bvecs", "--query", "q.bvecs", "--gpu_ids", "0 1 3", "--grid_search", "--measure", "cosine"])
+    assert a.gpus == [0, 1, 3] and a.grid_search and a.measure == "cosine"
+    assert B.tau_values(False) == [0.34, 0.41, 0.51, 0.64]
+    g = B.tau_values(True)
+    assert len(g) == 84 and g[0] == 0.0 and abs(g[69] - 0.69) < 1e-9 and abs(g[70] - 0.7) < 1e-9 and abs(g[-1] - 2.0) < 1e-9
+    assert B.dataset_class(ggnn, "x.bvecs") is ggnn.UCharDataset and B.dataset_class(ggnn, "x.ivecs") is ggnn.IntDataset
+    with pytest.raises(SystemExit):
+        B.dataset_class(ggnn, "x.txt")
