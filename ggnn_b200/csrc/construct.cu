@@ -1136,8 +1136,7 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
   int rc = -1;
 #define G200_MERGE(NS_, FAST_, D32_, NW_) \
   rc = launch_warp_kernel(merge_kernel<NS_, FAST_, D32_, NW_>, a, a.N_btm, smem, stream, "merge_kernel", true)
-  if (g4 && a.pl.stage_rows == 16 && a.pl.stage_mode == 0) {
-    if (int rc2 = make_row_gather_tensor_map(&a.tmap, d_base, cfg->N, cfg->D)) return rc2;
+  if (g4 && a.pl.stage_rows == 16 && a.pl.stage_mode == 0 && make_row_gather_tensor_map(&a.tmap, d_base, cfg->N, cfg->D) == 0) {
     a.pad_row = static_cast<int32_t>(cfg->N);  // out of bounds: zero fill, no memory traffic
     if (f.d32 == 3) rc = launch_warp_kernel(merge_kernel<2, true, 3, 1, true>, a, a.N_btm, smem, stream, "merge_kernel", true);
     else rc = launch_warp_kernel(merge_kernel<2, true, 4, 1, true>, a, a.N_btm, smem, stream, "merge_kernel", true);
@@ -1205,8 +1204,8 @@ extern "C" int ggnn_b200_sym(const ggnn_b200_graph_config* cfg, const float* d_b
   const int NS = a.sorted / 32;
   f.fast = f.fast && f.nw == 2 && NS == 2;
   if (int rc = make_plan(a.pl, a.D, !f.fast, !f.fast, a.sorted, a.cache, a.max_iterations, 16)) return rc;
-  if (f.fast && a.pl.stage_mode == 0 && a.D <= 256 && env_u32("GGNN_B200_BUILD_STAGE_MODE", 3) == 3) {
-    if (int rc = make_row_gather_tensor_map(&a.tmap, d_base, cfg->N, cfg->D)) return rc;
+  if (f.fast && a.pl.stage_mode == 0 && a.D <= 256 && env_u32("GGNN_B200_BUILD_STAGE_MODE", 3) == 3 &&
+      make_row_gather_tensor_map(&a.tmap, d_base, cfg->N, cfg->D) == 0) {
     a.pad_row = static_cast<int32_t>(cfg->N);  // out of bounds: zero fill, no memory traffic
     a.pl.stage_mode = 3;
   }

@@ -237,9 +237,12 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   a.stage_mode = (p.D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 3);
   if (a.stage_mode == 3) {  // TMA tile::gather4 row staging: register-resident fast kernels with pipelined 8-row groups only
     if (fast && rows >= 16 && (NI == 3 || NI == 4)) {  // the instantiated gather4 variants (two 8-row buffers)
-      rows = 16;
-      if (int rc = make_row_gather_tensor_map(&a.tmap, p.d_base, static_cast<uint64_t>(p.N_base), p.D)) return rc;
-      a.pad_row = env_u32("GGNN_B200_GATHER4_PAD_VALID", 0) ? 0 : p.N_base;  // out of bounds: zero fill, no memory traffic
+      // (a driver without cuTensorMapEncodeTiled: stay with one bulk copy per row)
+      if (make_row_gather_tensor_map(&a.tmap, p.d_base, static_cast<uint64_t>(p.N_base), p.D) == 0) {
+        rows = 16;
+        a.pad_row = env_u32("GGNN_B200_GATHER4_PAD_VALID", 0) ? 0 : p.N_base;  // out of bounds: zero fill, no memory traffic
+      }
+      else a.stage_mode = 0;
     }
     else a.stage_mode = 0;
   }
