@@ -295,3 +295,23 @@ def test_benchmark_cli_mirrors_the_reference_flags():
     assert B.dataset_class(ggnn, "x.bvecs") is ggnn.UCharDataset and B.dataset_class(ggnn, "x.ivecs") is ggnn.IntDataset
     with pytest.raises(SystemExit):
         B.dataset_class(ggnn, "x.txt")
+
+
+def test_import_ggnn_compat_package_and_reference_python_examples_start():
+    """compat/python/ggnn re-exports the API under the reference's module name; the reference's own example scripts
+    (only present in the build container) run unchanged up to the first call that needs a GPU"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "compat", "python") + os.pathsep + root)
+    code = ("import ggnn; assert ggnn.GGNN and ggnn.DistanceMeasure.Cosine == 1 and ggnn.Evaluator and ggnn.FloatDataset "
+            "and ggnn.UCharDataset and ggnn.IntDataset and callable(ggnn.set_log_level); print(ggnn.__version__)")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and "b200" in out.stdout, out.stderr
+    ex = "/root/reference/examples/python"
+    if not os.path.isdir(ex) or torch.cuda.is_available():
+        return
+    for script in ("ggnn_pytorch.py", "ggnn_pytorch_multi_gpu.py"):
+        p = subprocess.run([sys.executable, os.path.join(ex, script)], env=env, capture_output=True, text=True, timeout=300)
+        # no GPU here: the scripts get as far as build(), which refuses to run without a CUDA device
+        assert p.returncode != 0 and "no CPU fallback" in p.stderr, p.stderr[-500:]
