@@ -1,4 +1,4 @@
-"""world_size-2 gloo test of the sharded search plumbing (rank->rows mapping, query broadcast, all-gather of
+"""world_size-2 gloo test of the sharded search plumbing (rank->rows mapping, query broadcast or replication, all-gather of
 the per-rank top-K lists, id re-basing).  The per-shard search and the merge are stood in for by the CPU
 oracle here (tests only); on GPUs they are the CUDA kernels (tests/test_gpu_parity.py, bench.py --gpus N)."""
 import os
@@ -45,6 +45,14 @@ def _worker(rank, world, port, out_dir):
     ids, dists = D.distributed_query(local_query, merge, q, K, hi - lo)
     gi, gd = O.bf_query(base, query_full, K)
     ok = bool(np.array_equal(ids.numpy(), gi) and np.array_equal(dists.numpy(), gd) and torch.equal(q, torch.from_numpy(query_full)))
+    # replicated queries (bench.py default at N > 1: every rank already holds the batch, no broadcast): same result,
+    # and a rank whose copy differs is NOT overwritten (there is no hidden collective on the input side)
+    q_rep = torch.from_numpy(query_full.copy())
+    ids2, dists2 = D.distributed_query(local_query, merge, q_rep, K, hi - lo, broadcast=False)
+    ok = ok and bool(np.array_equal(ids2.numpy(), gi) and np.array_equal(dists2.numpy(), gd))
+    marker = torch.full((Nq, Dm), float(rank))
+    D.distributed_query(lambda qt: local_query(torch.from_numpy(query_full.copy())), merge, marker, K, hi - lo, broadcast=False)
+    ok = ok and bool((marker == float(rank)).all())
     open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "mismatch")
     dist.destroy_process_group()
 
