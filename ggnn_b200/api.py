@@ -561,14 +561,18 @@ class _Dataset:
 
     @classmethod
     def load(cls, file, from_=0, num=2 ** 32 - 1, pin_memory=False):
-        raw = np.fromfile(file, dtype=np.uint8)
-        d = int(raw[:4].view(np.int32)[0])
+        # memory-mapped: only the requested rows are read (a subset of a billion-vector file stays cheap)
+        raw = np.memmap(file, dtype=np.uint8, mode="r")
+        d = int(np.frombuffer(raw[:4].tobytes(), dtype=np.int32)[0])
         esz = np.dtype(cls.np_dtype).itemsize
         rec = 4 + d * esz
         n_total = raw.size // rec
         lo, hi = min(from_, n_total), min(n_total, from_ + num)
-        body = raw[:n_total * rec].reshape(n_total, rec)[lo:hi, 4:]
+        if num != 2 ** 32 - 1 and hi - lo != num:
+            raise ValueError("Dataset contains fewer vectors than requested.")  # dataset.cu:158-161 (CHECK_EQ there)
+        body = raw[lo * rec:hi * rec].reshape(hi - lo, rec)[:, 4:]
         t = torch.from_numpy(np.ascontiguousarray(body).view(cls.np_dtype).reshape(hi - lo, d).copy())
+        del raw
         if pin_memory and torch.cuda.is_available():
             t = t.pin_memory()
         return cls(t)

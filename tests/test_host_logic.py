@@ -315,3 +315,21 @@ def test_import_ggnn_compat_package_and_reference_python_examples_start():
         p = subprocess.run([sys.executable, os.path.join(ex, script)], env=env, capture_output=True, text=True, timeout=300)
         # no GPU here: the scripts get as far as build(), which refuses to run without a CUDA device
         assert p.returncode != 0 and "no CPU fallback" in p.stderr, p.stderr[-500:]
+
+
+def test_dataset_load_ranges_and_errors(tmp_path):
+    """subset loading reads only the requested rows; asking for more rows than the file holds is an error like in the
+    reference (src/ggnn/base/dataset.cu:158-161)"""
+    x = torch.arange(40, dtype=torch.float32).view(10, 4)
+    p = os.path.join(tmp_path, "x.fvecs")
+    ggnn.FloatDataset(x).store(p)
+    assert torch.equal(ggnn.FloatDataset.load(p, 3, 4).tensor, x[3:7])
+    assert torch.equal(ggnn.FloatDataset.load(p, 9, 1).tensor, x[9:])
+    assert torch.equal(ggnn.FloatDataset.load(p, 6).tensor, x[6:])          # num = all remaining rows
+    with pytest.raises(ValueError):
+        ggnn.FloatDataset.load(p, 8, 5)
+    u = torch.randint(0, 256, (6, 16), dtype=torch.uint8)
+    pb = os.path.join(tmp_path, "u.bvecs")
+    ggnn.UCharDataset(u).store(pb)
+    assert os.path.getsize(pb) == 6 * (4 + 16)
+    assert torch.equal(ggnn.UCharDataset.load(pb, 2, 3).tensor, u[2:5])
