@@ -38,6 +38,10 @@ class QueryParams(C.Structure):
         ("d_starting_points", C.c_void_p), ("d_nn1_stats", C.c_void_p), ("d_query_results", C.c_void_p),
         ("d_query_results_dists", C.c_void_p), ("d_stats", C.c_void_p),
         ("shards_per_gpu", C.c_uint32), ("on_gpu_shard_id", C.c_uint32), ("d_work_counter", C.c_void_p),
+        # fused shard-merge exchange (all zero = off)
+        ("n_scatter", C.c_uint32), ("scatter_slot", C.c_uint32), ("scatter_rows", C.c_uint32),
+        ("scatter_dists_offset", C.c_size_t), ("d_scatter_dst", C.c_void_p), ("d_scatter_flags", C.c_void_p),
+        ("d_scatter_done", C.c_void_p),
     ]
 
 
@@ -55,6 +59,8 @@ EXPORTS = [
     "ggnn_b200_query", "ggnn_b200_bf_query", "ggnn_b200_bf_query_workspace_bytes", "ggnn_b200_top", "ggnn_b200_nn1_stats", "ggnn_b200_select",
     "ggnn_b200_merge", "ggnn_b200_sym", "ggnn_b200_sym_buffer_merge", "ggnn_b200_build_graph",
     "ggnn_b200_merge_topk", "ggnn_b200_widen_u8",
+    "ggnn_b200_ipc_alloc", "ggnn_b200_ipc_open", "ggnn_b200_ipc_close", "ggnn_b200_ipc_free", "ggnn_b200_peer_enable",
+    "ggnn_b200_wait_flag",
 ]
 
 _lib = None
@@ -96,6 +102,12 @@ def lib():
         l.ggnn_b200_build_graph.argtypes = [cfgp, vp, i32, f32, u32, vp, vp, vp, sz, vp]
         l.ggnn_b200_merge_topk.argtypes = [vp, vp, u32, sz, sz, u32, u32, u32, C.c_int64, vp, vp, vp]
         l.ggnn_b200_widen_u8.argtypes = [vp, vp, sz, vp]
+        l.ggnn_b200_ipc_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
+        l.ggnn_b200_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        l.ggnn_b200_ipc_close.argtypes = [vp]
+        l.ggnn_b200_ipc_free.argtypes = [vp]
+        l.ggnn_b200_peer_enable.argtypes = [C.c_int]
+        l.ggnn_b200_wait_flag.argtypes = [vp, u32, u32, vp, vp]
         _lib = l
     return _lib
 

@@ -129,7 +129,6 @@ class GGNN:
         self._host_streams = {}
         self._host_rr = 0
         self._pools = []          # per GPU: swap.ShardPool or None (all shards resident)
-        self._query_calls = 0
 
     # ---- configuration (ggnn.cu:53-60, 420-454) ----
     def set_working_directory(self, path):
@@ -306,22 +305,27 @@ class GGNN:
             self._work_counters[key] = torch.zeros(1, dtype=torch.int32, device=device)
         return self._work_counters[key]
 
-    def _query_device(self, gpu_index, q_dev, k_query, tau_query, max_iterations, measure):
-        """all shards of one GPU -> sorted [Nq, K] ids (GPU-local numbering) + dists on that GPU"""
+    def _query_device(self, gpu_index, q_dev, k_query, tau_query, max_iterations, measure, scatter=None):
+        """all shards of one GPU -> sorted [Nq, K] ids (GPU-local numbering) + dists on that GPU.
+        scatter (exchange.ScatterTarget): the kernels store their lists (shard-local ids) straight into the gathered
+        buffers of the destination GPUs instead (fused shard-merge exchange) and nothing is returned"""
         l = _lib.lib()
         shards = self._shards[gpu_index * self._spg:(gpu_index + 1) * self._spg]
         dev = shards[0].device
         Nq = q_dev.shape[0]
         with torch.cuda.device(dev):
-            ids = torch.empty((Nq, k_query * self._spg), dtype=torch.int32, device=dev)
-            dists = torch.empty((Nq, k_query * self._spg), dtype=torch.float32, device=dev)
+            ids = dists = None
+            if scatter is None:
+                ids = torch.empty((Nq, k_query * self._spg), dtype=torch.int32, device=dev)
+                dists = torch.empty((Nq, k_query * self._spg), dtype=torch.float32, device=dev)
             order = list(range(len(shards)))
-            if shards[0].pool is not None:
+            pool = shards[0].pool
+            if pool is not None:
                 # swap mode: alternate the direction from call to call, so that the shards left on the GPU by the
-                # previous call are searched first (gpu_instance.cu:669-670, 740)
-                if self._query_calls % 2:
+                # previous call are searched first (gpu_instance.cu:669-670, 740); one counter per GPU (pool)
+                if pool.query_calls % 2:
                     order.reverse()
-                self._query_calls += 1
+                pool.query_calls += 1
             for oi, s in enumerate(order):
                 sh = shards[s]
                 sh_base, sh_graph = self._resident(sh)
@@ -337,10 +341,15 @@ class GGNN:
                 p.d_graph = sh_graph.graph.data_ptr()
                 p.d_starting_points = sh_graph.layer_translation(_lib.L - 1).data_ptr()
                 p.d_nn1_stats = sh_graph.nn1_stats.data_ptr()
-                p.d_query_results, p.d_query_results_dists = ids.data_ptr(), dists.data_ptr()
-                p.shards_per_gpu, p.on_gpu_shard_id = self._spg, s
+                if scatter is None:
+                    p.d_query_results, p.d_query_results_dists = ids.data_ptr(), dists.data_ptr()
+                    p.shards_per_gpu, p.on_gpu_shard_id = self._spg, s
+                else:
+                    scatter.apply(p, s)
                 p.d_work_counter = self._counter(dev).data_ptr()
                 _lib.check(l.ggnn_b200_query(C.byref(p), Nq, _stream_ptr(dev)))
+            if scatter is not None:
+                return None
             if self._spg > 1:  # replaces the segmented sort gpu_instance.cu:745-790
                 out_i = torch.empty((Nq, k_query), dtype=torch.int32, device=dev)
                 out_d = torch.empty((Nq, k_query), dtype=torch.float32, device=dev)
@@ -362,20 +371,27 @@ class GGNN:
         l = _lib.lib()
         k_query = int(k_query)
         n_gpus = len(self._gpus)
-        if self._results_on_gpu and n_gpus > 1:
-            raise RuntimeError("Returning query results on GPU is only possible when using a single GPU.")
+        # (the reference refuses results on the GPU for several GPUs, ggnn.cu:299-306: its merge runs on the CPU.  Here the
+        # merged lists live on the first GPU, so the flag is honoured for any number of GPUs.)
         if n_gpus == 1 and not self._results_on_gpu and not query.is_cuda:
             chunks = int(os.environ.get("GGNN_B200_QUERY_CHUNKS", "0")) or (2 if query.shape[0] >= 4096 else 1)
+            if self._pools and self._pools[0] is not None:
+                chunks = 1  # swap mode: one stream at a time owns the shard slots (see swap.ShardPool)
             return self._enqueue_host_query(query, k_query, tau_query, max_iterations, measure, chunks).result()
+        dev0 = self._shards[0].device
+        gather = self._local_gather(query.shape[0], k_query) if n_gpus > 1 else None
         per_gpu = []
         for gi in range(n_gpus):
             dev = self._shards[gi * self._spg].device
             q_dev = query.to(dev, non_blocking=True).contiguous()
-            per_gpu.append(self._query_device(gi, q_dev, k_query, tau_query, max_iterations, measure))
-        dev0 = self._shards[0].device
+            per_gpu.append(self._query_device(gi, q_dev, k_query, tau_query, max_iterations, measure,
+                                              scatter=gather.target(gi) if gather else None))
         if n_gpus == 1:
             ids, dists = per_gpu[0]
-        else:  # replaces ResultMerger::merge (result_merger.cpp:51-149): peer copies + one merge kernel
+        elif gather is not None:
+            # fused shard-merge exchange: every GPU's kernels stored their lists into the first GPU's buffer (peer stores)
+            ids, dists = gather.merge(query.shape[0], self._n_shard)
+        else:  # no peer access: peer copies + one merge kernel (replaces ResultMerger::merge, result_merger.cpp:51-149)
             with torch.cuda.device(dev0):
                 Nq = query.shape[0]
                 all_i = torch.empty((n_gpus, Nq, k_query), dtype=torch.int32, device=dev0)
@@ -392,6 +408,24 @@ class GGNN:
         if self._results_on_gpu:
             return ids, dists
         return ids.cpu(), dists.cpu()
+
+    def _local_gather(self, n_query, k_query):
+        """exchange.LocalGather for this (Nq, K), or None when the GPUs cannot access each other's memory"""
+        from . import exchange
+        key = (int(n_query), int(k_query))
+        cache = self.__dict__.setdefault("_gathers", {})
+        if key not in cache:
+            if os.environ.get("GGNN_B200_NO_PEER_GATHER"):
+                cache[key] = None
+            else:
+                try:
+                    cache.clear()  # one buffer at a time
+                    cache[key] = exchange.LocalGather([self._shards[g * self._spg].device for g in range(len(self._gpus))],
+                                                      n_query, k_query, self._spg)
+                except (NotImplementedError, _lib.GGNNError) as e:
+                    _log(1, f"peer gather unavailable ({e}); using peer copies")
+                    cache[key] = None
+        return cache[key]
 
     def query_async(self, query, k_query, tau_query, max_iterations=400, measure=DistanceMeasure.Euclidean):
         """query() for a HOST query tensor on a single GPU without waiting: the host->device copy, the traversal and
@@ -453,13 +487,22 @@ class GGNN:
         if query.dtype == torch.uint8:
             query = query.float()
         dev = torch.device("cuda", self._gpus[0])
-        l = _lib.lib()
         with torch.cuda.device(dev):
             if self._shards and len(self._shards) == 1 and self._shards[0].pool is None:
                 base = self._shards[0].base
             else:
                 base = self._base.to(dev).contiguous()
-            q = query.to(dev).contiguous()
+            ids, dists = self._bf_query_rows(base, query.to(dev).contiguous(), int(k_gt), int(measure))
+        if self._results_on_gpu:
+            return ids, dists
+        return ids.cpu(), dists.cpu()
+
+    @staticmethod
+    def _bf_query_rows(base, q, k_gt, measure=0):
+        """exact kNN of device-resident queries against device-resident base rows (any row range of a base)"""
+        l = _lib.lib()
+        dev = base.device
+        with torch.cuda.device(dev):
             Nq = q.shape[0]
             ids = torch.empty((Nq, k_gt), dtype=torch.int32, device=dev)
             dists = torch.empty((Nq, k_gt), dtype=torch.float32, device=dev)
@@ -474,9 +517,7 @@ class GGNN:
             _lib.check(l.ggnn_b200_bf_query(C.byref(p), Nq, _stream_ptr(dev)))
             if ws is not None:
                 ws.record_stream(torch.cuda.current_stream(dev))
-        if self._results_on_gpu:
-            return ids, dists
-        return ids.cpu(), dists.cpu()
+        return ids, dists
 
 
 class Evaluation:  # include/ggnn/base/eval.h:39-48, nanobind.cu:280-293

@@ -537,6 +537,7 @@ struct SymArgs {
   uint32_t sorted, cache, max_iterations;
   WarpPlan pl;
   int32_t pad_row;        // gather4 staging (see traverse.cuh); stage_mode 3 in `pl` switches it on
+  uint32_t serial;        // 1: one warp, points in order (deterministic; testing)
   TensorMapStorage tmap;
 };
 
@@ -738,7 +739,9 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ Sy
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const uint32_t n = blockIdx.x * CW + warp;
+  // serial mode (testing, GGNN_B200_SYM_SERIAL=1): ONE warp walks all points in order -- the deterministic schedule of
+  // the CPU oracle (the reference's own order is a race: cross-block atomics and reads of a buffer being written)
+  uint32_t n = a.serial ? (blockIdx.x == 0 && warp == 0 ? 0u : a.N_layer) : blockIdx.x * CW + warp;
   if (n >= a.N_layer) return;
   unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * a.pl.warp_smem_bytes;
   WarpSmem ws;
@@ -753,6 +756,11 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ Sy
   const float mean_nn1 = a.nn1_stats[0];
   const float xi = (a.measure == 0) ? __fmul_rn(__fmul_rn(__fmul_rn(mean_nn1, mean_nn1), a.tau_build), a.tau_build)
                                     : __fmul_rn(mean_nn1, a.tau_build);
+  for (; n < a.N_layer; n += a.serial ? 1u : a.N_layer) {
+  if (a.serial) {
+    __threadfence();  // the previous point's sym_buffer / sym_atomic writes (lane 0) are visible to every lane's loads
+    __syncwarp();
+  }
   const int m = a.translation ? a.translation[n] : static_cast<int>(n);
   SymVec<FAST, D32, NW> sv;
   sv.cfg = DistCfg{a.D, a.VB, a.items, a.measure};
@@ -910,8 +918,13 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ Sy
           break;
         }
       }
+      if (a.serial) {
+        __threadfence();
+        __syncwarp();
+      }
     }
   }
+  }  // points of this warp (one, unless serial)
 }
 
 // ================================================================================================
@@ -1210,8 +1223,9 @@ extern "C" int ggnn_b200_sym(const ggnn_b200_graph_config* cfg, const float* d_b
     a.pl.stage_mode = 3;
   }
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
+  a.serial = env_u32("GGNN_B200_SYM_SERIAL", 0) ? 1u : 0u;
 #define G200_SYM(NS_, FAST_, D32_, NW_) \
-  return launch_warp_kernel(sym_kernel<NS_, FAST_, D32_, NW_>, a, a.N_layer, smem, stream, "sym_kernel")
+  return launch_warp_kernel(sym_kernel<NS_, FAST_, D32_, NW_>, a, a.serial ? 1u : a.N_layer, smem, stream, "sym_kernel")
   if (f.fast) {
     switch (f.d32) {
       case 1: G200_SYM(2, true, 1, 2);

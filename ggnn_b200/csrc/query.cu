@@ -120,10 +120,22 @@ __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) qu
     }
 
     // :81-90 (+ simple_knn_cache.cuh:344-352)
-    const size_t row = (static_cast<size_t>(n) * p.shards_per_gpu + p.on_gpu_shard_id) * p.KQuery;
-    const int id_off = static_cast<int>(p.on_gpu_shard_id) * p.N_base;
-    L.write_results(p.d_query_results + row, p.d_query_results_dists ? p.d_query_results_dists + row : nullptr, p.KQuery,
-                    id_off);
+    if (p.d_query_results) {
+      const size_t row = (static_cast<size_t>(n) * p.shards_per_gpu + p.on_gpu_shard_id) * p.KQuery;
+      const int id_off = static_cast<int>(p.on_gpu_shard_id) * p.N_base;
+      L.write_results(p.d_query_results + row, p.d_query_results_dists ? p.d_query_results_dists + row : nullptr, p.KQuery,
+                      id_off);
+    }
+    // fused shard-merge exchange: this query's list goes straight into every destination GPU's gathered buffer
+    // (peer-mapped memory: the stores travel over NVLink while the other warps keep traversing)
+    if (p.n_scatter) {
+      const size_t srow = (static_cast<size_t>(p.scatter_slot) * p.scatter_rows + n) * p.KQuery;
+      for (uint32_t t = 0; t < p.n_scatter; ++t) {
+        char* dst = static_cast<char*>(p.d_scatter_dst[t]);
+        L.write_results(reinterpret_cast<int*>(dst) + srow, reinterpret_cast<float*>(dst + p.scatter_dists_offset) + srow,
+                        p.KQuery, 0);
+      }
+    }
     if (p.d_stats && lane == 0) {
       p.d_stats[2 * static_cast<size_t>(n)] = st.pops;
       p.d_stats[2 * static_cast<size_t>(n) + 1] = st.dists;
@@ -135,6 +147,21 @@ __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) qu
     }
     else {
       n += total_warps;
+    }
+  }
+
+  // exchange: the last warp of the launch to get here bumps the flag word of every destination; every warp's result
+  // stores are ordered before its count (system-scope fence), the count before the flags
+  if (p.n_scatter && p.d_scatter_done) {
+    __threadfence_system();
+    unsigned old = 0;
+    if (lane == 0) old = atomicAdd(p.d_scatter_done, 1u);
+    old = __shfl_sync(FULL, old, 0);
+    if (old == total_warps - 1) {
+      if (lane == 0) *p.d_scatter_done = 0;  // ready for the next launch on this stream
+      __threadfence_system();
+      if (p.d_scatter_flags)
+        for (uint32_t t = lane; t < p.n_scatter; t += 32) atomicAdd_system(p.d_scatter_flags[t], 1u);
     }
   }
 }
@@ -179,8 +206,10 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   QueryArgs a{};
   a.p = *pin;
   ggnn_b200_query_params& p = a.p;
-  if (!p.d_base || !p.d_query || !p.d_graph || !p.d_starting_points || !p.d_nn1_stats || !p.d_query_results)
+  if (!p.d_base || !p.d_query || !p.d_graph || !p.d_starting_points || !p.d_nn1_stats || (!p.d_query_results && !p.n_scatter))
     return set_error(GGNN_B200_ERR_INVALID, "null device pointer");
+  if (p.n_scatter && (!p.d_scatter_dst || p.scatter_rows < N_query))
+    return set_error(GGNN_B200_ERR_INVALID, "scatter: need destination pointers and scatter_rows >= N_query");
   if (p.measure != GGNN_B200_EUCLIDEAN && p.measure != GGNN_B200_COSINE)
     return set_error(GGNN_B200_ERR_INVALID, "unknown distance measure");
   if (p.shards_per_gpu == 0) p.shards_per_gpu = 1;

@@ -11,6 +11,8 @@ bytes per rank) and merged by one kernel (ggnn_b200_merge_topk) -- no collective
 import torch
 import torch.distributed as dist
 
+from .exchange import make_exchange, PeerExchange, NcclExchange  # noqa: F401  (the device-side exchange)
+
 
 def shard_layout(N, n_shard, world_size):
     """-> (num_shards, shards_per_gpu); same preconditions as the reference (ggnn.cu:162-183)."""
@@ -47,6 +49,16 @@ def distributed_query(local_query_fn, merge_fn, query, k, rows_per_rank, group=N
     gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int32, device=ids.device)
     dist.all_gather(list(gathered.unbind(0)), packed, group=group)
     return merge_fn(gathered[:, 0], gathered[:, 1].view(torch.float32), rows_per_rank)
+
+
+def exchange_query(idx, exchange, q_dev, k, tau_query, max_iterations=400, measure=0, pipe=0):
+    """One batch of the sharded search through the fused exchange (ggnn_b200/exchange.py): the traversal kernels of this
+    rank's shards store their lists into every rank's gathered buffer, then this rank waits for everybody's lists and
+    merges them.  -> (ids [Nq, k] global numbering, dists) on this rank's GPU; every rank gets the full result.
+    All ranks must call this in the same order with the same `pipe`."""
+    tgt, b = exchange.target(pipe)
+    idx._query_device(0, q_dev, int(k), tau_query, max_iterations, measure, scatter=tgt)
+    return exchange.finish(pipe, b, q_dev.shape[0], idx._n_shard)
 
 
 def gpu_merge(all_ids, all_dists, id_offset_per_list, k=None):

@@ -54,7 +54,9 @@ class ShardPool:
         self.host_blob = {}               # shard id -> pinned host tensor
         self.on_disk = set()
         self.has_graph = set()            # shards that have a graph anywhere
-        self.ready = {}                   # shard id -> event of its (possibly still running) load
+        self.ready = {}                   # shard id -> event of its load; kept until the shard is evicted, so that EVERY
+                                          # stream that acquires the shard waits for the load (not only the first one)
+        self.query_calls = 0              # direction toggle of this GPU's shard loop (gpu_instance.cu:669-670)
         self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self.stats = {"loads": 0, "evictions": 0, "writebacks": 0, "disk_writes": 0, "disk_reads": 0}
 
@@ -100,11 +102,11 @@ class ShardPool:
         slot = self.resident.pop(victim)
         self.stats["evictions"] += 1
         if self.device.type == "cuda":
-            # the victim's kernels (compute stream) and its own load must be done before the slot is overwritten
-            torch.cuda.current_stream(self.device).synchronize()
-            ev = self.ready.pop(victim, None)
-            if ev is not None:
-                ev.synchronize()
+            # Kernels of ANY stream may still read the victim (GGNN.query() pipelines chunks over several internal
+            # streams, query_async keeps batches in flight) and its own load may still be running: wait for the whole
+            # device before the slot is overwritten.  (Swapping is bound by the host->device copies, not by this.)
+            torch.cuda.synchronize(self.device)
+            self.ready.pop(victim, None)
         if victim in self.dirty:
             self._writeback(victim, slot)
         return slot
@@ -132,7 +134,7 @@ class ShardPool:
         if gid not in self.resident:
             raise RuntimeError("no GPU shard buffer available")
         self.resident.move_to_end(gid)
-        ev = self.ready.pop(gid, None)
+        ev = self.ready.get(gid)
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
         return self.slots[self.resident[gid]]
@@ -148,6 +150,9 @@ class ShardPool:
         self.dirty.discard(gid)
         self.host_blob.pop(gid, None)
         if gid in self.resident:                      # drop a stale device copy
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            self.ready.pop(gid, None)
             self.free.append(self.resident.pop(gid))
 
     def blob_to_file(self, gid, path):

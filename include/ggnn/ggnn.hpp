@@ -8,8 +8,11 @@
 // Same names, argument meaning, defaults and error behaviour (std::runtime_error / std::out_of_range for API
 // misuse).  All computation happens in the sm_100a kernels behind the C ABI; there is no CPU fallback.
 // Differences: uint8 vectors are widened to fp32 once on the device (bit-identical results, see
-// ggnn_b200_widen_u8), shards stay resident in HBM (no swap to host / disk), multi-GPU results are merged on
-// the first GPU by a kernel instead of the reference's CPU heap merge.
+// ggnn_b200_widen_u8); multi-GPU results are merged on the first GPU by a kernel -- the traversal kernels store their
+// lists straight into its memory (peer access) -- instead of the reference's CPU heap merge, so results may stay on the
+// GPU for any number of GPUs; queryAsync() keeps several host batches in flight.  Shards that do not fit on their GPU
+// are swapped GPU <-> pinned host memory <-> part_<id>.ggnn files like the reference does (setCPUMemoryLimit /
+// setReservedGPUMemory, src/ggnn/base/gpu_instance.cu:135-227, 370-467).
 #pragma once
 
 #include <ggnn_b200.h>
@@ -550,62 +553,89 @@ class GGNN {
   using Graph = ggnn::Graph<KeyT, ValueT>;
   static constexpr uint32_t MIN_D = 1, MAX_D = 4096, MIN_KBUILD = 2, MAX_KBUILD = 512;
 
-  GGNN() = default;
-  ~GGNN()
-  {
-    for (auto& sh : shards) {
-      cudaSetDevice(sh.gpu);
-      if (sh.stream) cudaStreamDestroy(sh.stream);
-      if (sh.work_counter) cudaFree(sh.work_counter);
+  /// A query enqueued by queryAsync(): get() waits for it and hands out the results (pinned host memory).
+  class QueryHandle {
+   public:
+    QueryHandle() = default;
+    QueryHandle(QueryHandle&&) noexcept = default;
+    QueryHandle& operator=(QueryHandle&&) noexcept = default;
+    [[nodiscard]] bool valid() const { return event != nullptr; }
+    [[nodiscard]] bool done() const { return !event || cudaEventQuery(event) == cudaSuccess; }
+    [[nodiscard]] Results get()
+    {
+      if (event) detail::cuda_check(cudaEventSynchronize(event), "cudaEventSynchronize");
+      event = nullptr;
+      return std::move(results);
     }
-  }
+
+   private:
+    friend class GGNN;
+    Results results;
+    cudaEvent_t event{nullptr};  // owned by the GGNN instance's pipeline
+  };
+
+  GGNN() : st(std::make_unique<State>()) {}
+  ~GGNN() = default;
   GGNN(const GGNN&) = delete;
   GGNN& operator=(const GGNN&) = delete;
+  // all state lives behind one pointer: a moved GGNN keeps referring to its own base (the reference is movable too,
+  // include/ggnn/base/ggnn.cuh:55-58)
   GGNN(GGNN&&) noexcept = default;
   GGNN& operator=(GGNN&&) noexcept = default;
 
-  void setWorkingDirectory(const std::filesystem::path& dir) { graph_dir = dir; }
-  void setCPUMemoryLimit(size_t) {}      // shards stay resident in HBM
-  void setReservedGPUMemory(size_t) {}
+  void setWorkingDirectory(const std::filesystem::path& dir) { st->graph_dir = dir; }
+  /// host memory the swapped-out graphs may use; beyond it they live in part_<id>.ggnn files (gpu_instance.cu:177-200)
+  void setCPUMemoryLimit(size_t limit) { st->cpu_memory_limit = limit; }
+  /// GPU memory left free when counting how many shards fit on a GPU (gpu_instance.cu:150-175)
+  void setReservedGPUMemory(size_t reserved) { st->reserved_gpu_memory = reserved; }
   void setGPUs(const std::span<const int>& ids)
   {
-    if (!shards.empty()) throw std::runtime_error("GPUs cannot be changed after the graph has been set up.");
+    if (!st->shards.empty()) throw std::runtime_error("GPUs cannot be changed after the graph has been set up.");
     if (ids.empty()) throw std::out_of_range("at least one GPU is required");
-    gpu_ids.assign(ids.begin(), ids.end());
+    st->gpu_ids.assign(ids.begin(), ids.end());
   }
   void setGPUs(const std::vector<int>& ids) { setGPUs(std::span<const int>{ids.data(), ids.size()}); }
   void setShardSize(uint32_t n)
   {
-    if (!shards.empty()) throw std::runtime_error("The shard size cannot be changed after the graph has been set up.");
-    N_shard = n;
+    if (!st->shards.empty()) throw std::runtime_error("The shard size cannot be changed after the graph has been set up.");
+    st->N_shard = n;
   }
-  void setReturnResultsOnGPU(bool flag = true) { return_results_on_gpu = flag; }
+  /// (the reference allows this for one GPU only, ggnn.cu:299-306; here the merged lists live on the first GPU)
+  void setReturnResultsOnGPU(bool flag = true) { st->return_results_on_gpu = flag; }
 
   void setBase(GenericDataset&& b)
   {
     check_base(b);
-    owned_base = std::move(b);
-    base = &owned_base;
+    st->owned_base = std::move(b);
+    st->base = &st->owned_base;
   }
   void setBaseReference(const GenericDataset& b)
   {
     check_base(b);
-    base = &b;
+    st->base = &b;
   }
   void setBaseReference(GenericDataset&&) = delete;
 
   void build(uint32_t KBuild, float tau_build, uint32_t refinement_iterations = 2, DistanceMeasure measure = DistanceMeasure::Euclidean)
   {
     prepare(KBuild);
-    for (auto& sh : shards) {
-      detail::DeviceGuard g(sh.gpu);
-      const size_t scratch_bytes = ggnn_b200_build_scratch_bytes(&cfg);
+    State& s = *st;
+    for (auto& g : s.gpus) {
+      detail::DeviceGuard guard(g.id);
+      const size_t scratch_bytes = ggnn_b200_build_scratch_bytes(&s.cfg);
       void* scratch = nullptr;
       detail::cuda_check(cudaMalloc(&scratch, scratch_bytes), "cudaMalloc(build scratch)");
-      detail::cuda_check(cudaMemsetAsync(sh.graph.memory.data(), 0, sh.graph.memory.size_bytes(), sh.stream), "cudaMemsetAsync");
-      const int rc = ggnn_b200_build_graph(&cfg, sh.base.data(), static_cast<int>(measure), tau_build, refinement_iterations,
-                                           nullptr, sh.graph.memory.data(), scratch, scratch_bytes, sh.stream);
-      cudaStreamSynchronize(sh.stream);
+      int rc = 0;
+      for (uint32_t i = 0; i < s.spg && !rc; ++i) {
+        Shard& sh = s.shards[g.first_shard + i];
+        Slot& slot = acquire(g, sh);
+        detail::cuda_check(cudaMemsetAsync(slot.blob.data(), 0, slot.blob.size_bytes(), g.stream), "cudaMemsetAsync");
+        rc = ggnn_b200_build_graph(&s.cfg, slot.base.data(), static_cast<int>(measure), tau_build, refinement_iterations,
+                                   nullptr, slot.blob.data(), scratch, scratch_bytes, g.stream);
+        cudaStreamSynchronize(g.stream);
+        sh.has_graph = rc == 0;
+        sh.dirty = true;
+      }
       cudaFree(scratch);
       detail::abi_check(rc);
     }
@@ -613,119 +643,264 @@ class GGNN {
 
   void store()
   {
-    if (shards.empty()) throw std::runtime_error("There is no graph to store.");
-    std::filesystem::create_directories(graph_dir);
-    for (auto& sh : shards) {  // gpu_instance.cu:86-115: part_<global_shard_id>.ggnn = raw blob
-      std::vector<uint8_t> h(sh.graph.memory.size_bytes());
-      detail::DeviceGuard g(sh.gpu);
-      detail::cuda_check(cudaMemcpy(h.data(), sh.graph.memory.data(), h.size(), cudaMemcpyDeviceToHost), "cudaMemcpy");
-      std::ofstream f(graph_dir / ("part_" + std::to_string(sh.global_id) + ".ggnn"), std::ios::binary);
-      f.write(reinterpret_cast<const char*>(h.data()), static_cast<std::streamsize>(h.size()));
+    State& s = *st;
+    if (!has_graph()) throw std::runtime_error("There is no graph to store.");
+    std::filesystem::create_directories(s.graph_dir);
+    for (auto& g : s.gpus) {
+      detail::DeviceGuard guard(g.id);
+      for (uint32_t i = 0; i < s.spg; ++i) {  // gpu_instance.cu:86-115: part_<global_shard_id>.ggnn = raw blob
+        Shard& sh = s.shards[g.first_shard + i];
+        const auto path = part_path(sh.global_id);
+        if (sh.slot >= 0) {  // newest copy is on the GPU
+          std::vector<uint8_t> h(s.blob_bytes);
+          detail::cuda_check(cudaMemcpy(h.data(), g.slots[sh.slot].blob.data(), h.size(), cudaMemcpyDeviceToHost), "cudaMemcpy");
+          write_file(path, h.data(), h.size());
+        }
+        else if (sh.host_blob.data()) write_file(path, sh.host_blob.data(), s.blob_bytes);
+        // else: already on disk as part_<id>.ggnn
+      }
     }
   }
 
   void load(uint32_t KBuild)
   {
     prepare(KBuild);
-    for (auto& sh : shards) {
-      const auto path = graph_dir / ("part_" + std::to_string(sh.global_id) + ".ggnn");
-      if (!std::filesystem::exists(path) || std::filesystem::file_size(path) != sh.graph.memory.size_bytes())
-        throw std::runtime_error(path.string() + ": missing or unexpected file size");
-      std::vector<uint8_t> h(sh.graph.memory.size_bytes());
-      std::ifstream f(path, std::ios::binary);
-      f.read(reinterpret_cast<char*>(h.data()), static_cast<std::streamsize>(h.size()));
-      detail::DeviceGuard g(sh.gpu);
-      detail::cuda_check(cudaMemcpy(sh.graph.memory.data(), h.data(), h.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
+    State& s = *st;
+    for (auto& g : s.gpus) {
+      detail::DeviceGuard guard(g.id);
+      for (uint32_t i = 0; i < s.spg; ++i) {
+        Shard& sh = s.shards[g.first_shard + i];
+        const auto path = part_path(sh.global_id);
+        if (!std::filesystem::exists(path) || std::filesystem::file_size(path) != s.blob_bytes)
+          throw std::runtime_error(path.string() + ": missing or unexpected file size");  // gpu_instance.cu:454-455
+        if (g.swap) {  // read when the shard is swapped in
+          if (sh.slot >= 0) {
+            g.slots[sh.slot].resident = -1;
+            sh.slot = -1;
+          }
+          sh.host_blob = Dataset<uint8_t>{};
+          sh.on_disk = true;
+        }
+        else {
+          std::vector<uint8_t> h(s.blob_bytes);
+          read_file(path, h.data(), h.size());
+          detail::cuda_check(cudaMemcpy(g.slots[sh.slot].blob.data(), h.data(), h.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
+        }
+        sh.has_graph = true;
+        sh.dirty = false;
+      }
     }
   }
 
   [[nodiscard]] Results query(const GenericDataset& query, uint32_t KQuery, float tau_query, uint32_t max_iterations = 400,
                               DistanceMeasure measure = DistanceMeasure::Euclidean)
   {
-    if (shards.empty()) throw std::runtime_error("There is no graph to query.");
+    State& s = *st;
+    if (!has_graph()) throw std::runtime_error("There is no graph to query.");
     check_query(query, "unsupported datatype for query");
-    const uint32_t n_gpus = static_cast<uint32_t>(gpu_ids.size());
-    if (return_results_on_gpu && n_gpus > 1)
-      throw std::runtime_error("Returning query results on GPU is only possible when using a single GPU.");
+    const uint32_t n_gpus = static_cast<uint32_t>(s.gpus.size());
     const uint32_t Nq = static_cast<uint32_t>(query.N);
+    // one GPU, host query, host results, everything resident: the pipelined path (no allocation per call)
+    if (n_gpus == 1 && !s.return_results_on_gpu && query.isCPUAccessible() && !s.gpus[0].swap)
+      return queryAsync(query, KQuery, tau_query, max_iterations, measure).get();
+
+    // fused shard-merge exchange for several GPUs: every GPU's traversal kernels store their lists straight into one
+    // buffer on the first GPU (peer access); fall back to peer copies when the devices cannot see each other
+    const bool gather = n_gpus > 1 && s.peer_gather;
+    const uint32_t n_slots = n_gpus * s.spg;
+    const size_t list_words = static_cast<size_t>(Nq) * KQuery;
+    Gpu& g0 = s.gpus[0];
+    Dataset<KeyT> all;
+    if (gather) {
+      detail::DeviceGuard guard(g0.id);
+      all = Dataset<KeyT>::emptyOnGPU(static_cast<uint64_t>(2) * n_slots * Nq, KQuery, g0.id);
+    }
     std::vector<Dataset<KeyT>> ids(n_gpus);
     std::vector<Dataset<ValueT>> dists(n_gpus);
     std::vector<Dataset<float>> q_dev(n_gpus);
+    std::vector<cudaEvent_t> evs(n_gpus, nullptr);
     // launch everything asynchronously on every GPU first
     for (uint32_t gi = 0; gi < n_gpus; ++gi) {
-      const int gpu = gpu_ids[gi];
-      detail::DeviceGuard g(gpu);
-      cudaStream_t stream = shards[gi * spg].stream;
-      q_dev[gi] = float_on_gpu(query, gpu, stream);
-      const float* dq = q_dev[gi].data();
-      ids[gi] = Dataset<KeyT>::emptyOnGPU(Nq, KQuery * spg, gpu);
-      dists[gi] = Dataset<ValueT>::emptyOnGPU(Nq, KQuery * spg, gpu);
-      for (uint32_t s = 0; s < spg; ++s) {
-        Shard& sh = shards[gi * spg + s];
-        ggnn_b200_query_params p{};
-        p.D = cfg.D; p.measure = static_cast<int>(measure); p.KQuery = KQuery;
-        p.tau_query = tau_query; p.max_iterations = max_iterations;
-        p.N_base = static_cast<int32_t>(cfg.N); p.KBuild = cfg.KBuild; p.num_starting_points = cfg.S;
-        p.d_base = sh.base.data(); p.d_query = dq;
-        p.d_graph = sh.graph.graph();
-        p.d_starting_points = sh.graph.translation() + cfg.STs_offsets[GGNN_B200_L - 1];
-        p.d_nn1_stats = sh.graph.nn1_stats();
-        p.d_query_results = ids[gi].data(); p.d_query_results_dists = dists[gi].data();
-        p.shards_per_gpu = spg; p.on_gpu_shard_id = s;
-        p.d_work_counter = sh.work_counter;
-        detail::abi_check(ggnn_b200_query(&p, Nq, stream));
+      Gpu& g = s.gpus[gi];
+      detail::DeviceGuard guard(g.id);
+      q_dev[gi] = float_on_gpu(query, g.id, g.stream);
+      if (!gather) {
+        ids[gi] = Dataset<KeyT>::emptyOnGPU(Nq, KQuery * s.spg, g.id);
+        dists[gi] = Dataset<ValueT>::emptyOnGPU(Nq, KQuery * s.spg, g.id);
       }
-      if (spg > 1) {  // replaces gpu_instance.cu:745-790
-        Dataset<KeyT> mi = Dataset<KeyT>::emptyOnGPU(Nq, KQuery, gpu);
-        Dataset<ValueT> md = Dataset<ValueT>::emptyOnGPU(Nq, KQuery, gpu);
-        detail::abi_check(ggnn_b200_merge_topk(ids[gi].data(), dists[gi].data(), spg, KQuery, static_cast<size_t>(KQuery) * spg,
-                                               KQuery, Nq, KQuery, 0, mi.data(), md.data(), stream));
-        detail::cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");  // the inputs are freed below
+      else {
+        void* dst = all.data();
+        detail::cuda_check(cudaMemcpyAsync(g.d_gather_tbl, &dst, sizeof(void*), cudaMemcpyHostToDevice, g.stream), "cudaMemcpyAsync");
+      }
+      // swap mode: alternate the direction from call to call, so that the shards left on the GPU by the previous call
+      // are searched first (gpu_instance.cu:669-670, 740)
+      const bool reverse = g.swap && (g.query_calls++ % 2);
+      for (uint32_t i = 0; i < s.spg; ++i) {
+        const uint32_t sidx = reverse ? s.spg - 1 - i : i;
+        Shard& sh = s.shards[g.first_shard + sidx];
+        Slot& slot = acquire(g, sh);
+        ggnn_b200_query_params p = query_params(slot, q_dev[gi].data(), KQuery, tau_query, max_iterations, measure);
+        if (gather) {
+          p.n_scatter = 1;
+          p.scatter_slot = gi * s.spg + sidx;
+          p.scatter_rows = Nq;
+          p.scatter_dists_offset = static_cast<size_t>(n_slots) * list_words * sizeof(KeyT);
+          p.d_scatter_dst = reinterpret_cast<void* const*>(g.d_gather_tbl);
+        }
+        else {
+          p.d_query_results = ids[gi].data();
+          p.d_query_results_dists = dists[gi].data();
+          p.shards_per_gpu = s.spg;
+          p.on_gpu_shard_id = sidx;
+        }
+        p.d_work_counter = g.work_counter;
+        detail::abi_check(ggnn_b200_query(&p, Nq, g.stream));
+      }
+      if (!gather && s.spg > 1) {  // replaces gpu_instance.cu:745-790
+        Dataset<KeyT> mi = Dataset<KeyT>::emptyOnGPU(Nq, KQuery, g.id);
+        Dataset<ValueT> md = Dataset<ValueT>::emptyOnGPU(Nq, KQuery, g.id);
+        detail::abi_check(ggnn_b200_merge_topk(ids[gi].data(), dists[gi].data(), s.spg, KQuery, static_cast<size_t>(KQuery) * s.spg,
+                                               KQuery, Nq, KQuery, 0, mi.data(), md.data(), g.stream));
+        detail::cuda_check(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");  // the inputs are freed below
         ids[gi] = std::move(mi);
         dists[gi] = std::move(md);
+      }
+      if (gather && gi > 0) {
+        detail::cuda_check(cudaEventCreateWithFlags(&evs[gi], cudaEventDisableTiming), "cudaEventCreate");
+        detail::cuda_check(cudaEventRecord(evs[gi], g.stream), "cudaEventRecord");
       }
     }
     Results out;
     if (n_gpus == 1) {
-      detail::DeviceGuard g(gpu_ids[0]);
-      detail::cuda_check(cudaStreamSynchronize(shards[0].stream), "cudaStreamSynchronize");
+      detail::DeviceGuard guard(g0.id);
+      detail::cuda_check(cudaStreamSynchronize(g0.stream), "cudaStreamSynchronize");
       out.ids = std::move(ids[0]);
       out.dists = std::move(dists[0]);
     }
-    else {  // replaces ResultMerger::merge (result_merger.cpp:51-149): peer copies + one merge kernel on the first GPU
-      const int g0 = gpu_ids[0];
-      Dataset<KeyT> all_i = Dataset<KeyT>::emptyOnGPU(static_cast<uint64_t>(n_gpus) * Nq, KQuery, g0);
-      Dataset<ValueT> all_d = Dataset<ValueT>::emptyOnGPU(static_cast<uint64_t>(n_gpus) * Nq, KQuery, g0);
-      for (uint32_t gi = 0; gi < n_gpus; ++gi) {
-        detail::DeviceGuard g(gpu_ids[gi]);
-        cudaStream_t stream = shards[gi * spg].stream;
-        const size_t n = static_cast<size_t>(Nq) * KQuery;
-        detail::cuda_check(cudaMemcpyPeerAsync(all_i.data() + gi * n, g0, ids[gi].data(), gpu_ids[gi], n * sizeof(KeyT), stream), "cudaMemcpyPeerAsync");
-        detail::cuda_check(cudaMemcpyPeerAsync(all_d.data() + gi * n, g0, dists[gi].data(), gpu_ids[gi], n * sizeof(ValueT), stream), "cudaMemcpyPeerAsync");
-        detail::cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    else {  // replaces ResultMerger::merge (result_merger.cpp:51-149): one merge kernel on the first GPU
+      detail::DeviceGuard guard(g0.id);
+      const KeyT* src_i = nullptr;
+      const ValueT* src_d = nullptr;
+      Dataset<KeyT> all_i;
+      Dataset<ValueT> all_d;
+      uint32_t lists = n_gpus;
+      int64_t id_off = static_cast<int64_t>(s.spg) * s.cfg.N;
+      if (gather) {
+        for (uint32_t gi = 1; gi < n_gpus; ++gi) detail::cuda_check(cudaStreamWaitEvent(g0.stream, evs[gi], 0), "cudaStreamWaitEvent");
+        src_i = all.data();
+        src_d = reinterpret_cast<const ValueT*>(all.data() + static_cast<size_t>(n_slots) * list_words);
+        lists = n_slots;
+        id_off = s.cfg.N;
       }
-      detail::DeviceGuard g(g0);
-      out.ids = Dataset<KeyT>::emptyOnGPU(Nq, KQuery, g0);
-      out.dists = Dataset<ValueT>::emptyOnGPU(Nq, KQuery, g0);
-      detail::abi_check(ggnn_b200_merge_topk(all_i.data(), all_d.data(), n_gpus, static_cast<size_t>(Nq) * KQuery, KQuery, KQuery, Nq,
-                                             KQuery, static_cast<int64_t>(spg) * cfg.N, out.ids.data(), out.dists.data(), shards[0].stream));
-      detail::cuda_check(cudaStreamSynchronize(shards[0].stream), "cudaStreamSynchronize");
+      else {
+        all_i = Dataset<KeyT>::emptyOnGPU(static_cast<uint64_t>(n_gpus) * Nq, KQuery, g0.id);
+        all_d = Dataset<ValueT>::emptyOnGPU(static_cast<uint64_t>(n_gpus) * Nq, KQuery, g0.id);
+        for (uint32_t gi = 0; gi < n_gpus; ++gi) {
+          Gpu& g = s.gpus[gi];
+          detail::DeviceGuard guard_i(g.id);
+          detail::cuda_check(cudaMemcpyPeerAsync(all_i.data() + gi * list_words, g0.id, ids[gi].data(), g.id, list_words * sizeof(KeyT), g.stream), "cudaMemcpyPeerAsync");
+          detail::cuda_check(cudaMemcpyPeerAsync(all_d.data() + gi * list_words, g0.id, dists[gi].data(), g.id, list_words * sizeof(ValueT), g.stream), "cudaMemcpyPeerAsync");
+          detail::cuda_check(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");
+        }
+        src_i = all_i.data();
+        src_d = all_d.data();
+      }
+      out.ids = Dataset<KeyT>::emptyOnGPU(Nq, KQuery, g0.id);
+      out.dists = Dataset<ValueT>::emptyOnGPU(Nq, KQuery, g0.id);
+      detail::abi_check(ggnn_b200_merge_topk(src_i, src_d, lists, list_words, KQuery, KQuery, Nq, KQuery, id_off, out.ids.data(),
+                                             out.dists.data(), g0.stream));
+      detail::cuda_check(cudaStreamSynchronize(g0.stream), "cudaStreamSynchronize");
+      for (uint32_t gi = 1; gi < n_gpus; ++gi) {  // the other GPUs' query copies are freed on return
+        if (evs[gi]) cudaEventDestroy(evs[gi]);
+        detail::DeviceGuard guard_i(s.gpus[gi].id);
+        cudaStreamSynchronize(s.gpus[gi].stream);
+      }
     }
-    return return_results_on_gpu ? std::move(out) : to_host(std::move(out));
+    return s.return_results_on_gpu ? std::move(out) : to_host(std::move(out));
+  }
+
+  /// query() for a host-resident query on one GPU without waiting: host->device copy, traversal and device->host copy
+  /// of the results are enqueued on one of the instance's pipelines (own stream and device buffers, nothing is allocated
+  /// on the device per call); several batches may be in flight, their copies overlap the other batches' kernels.
+  /// (The reference's query is synchronous only: src/ggnn/base/ggnn.cu:506-551.)  `query` must stay valid until get().
+  [[nodiscard]] QueryHandle queryAsync(const GenericDataset& query, uint32_t KQuery, float tau_query, uint32_t max_iterations = 400,
+                                       DistanceMeasure measure = DistanceMeasure::Euclidean)
+  {
+    State& s = *st;
+    if (!has_graph()) throw std::runtime_error("There is no graph to query.");
+    check_query(query, "unsupported datatype for query");
+    if (s.gpus.size() != 1 || !query.isCPUAccessible() || s.gpus[0].swap)
+      throw std::runtime_error("queryAsync takes a host-resident query and a single GPU holding all of its shards.");
+    Gpu& g = s.gpus[0];
+    detail::DeviceGuard guard(g.id);
+    const uint32_t Nq = static_cast<uint32_t>(query.N);
+    if (g.pipes.empty()) {
+      g.pipes.resize(4);
+      for (auto& p : g.pipes) {
+        detail::cuda_check(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        detail::cuda_check(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming), "cudaEventCreate");
+        detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&p.work_counter), 16), "cudaMalloc");
+      }
+    }
+    Pipe& p = g.pipes[g.next_pipe++ % g.pipes.size()];
+    detail::cuda_check(cudaEventSynchronize(p.done), "cudaEventSynchronize");  // the batch that used this pipeline last is complete
+    const size_t q_bytes = static_cast<size_t>(Nq) * query.D * sizeof(float);
+    const size_t r_words = static_cast<size_t>(Nq) * KQuery * s.spg;
+    p.query.reserve(q_bytes);
+    p.ids.reserve(r_words * sizeof(KeyT));
+    p.dists.reserve(r_words * sizeof(ValueT));
+    const float* dq = static_cast<const float*>(p.query.ptr);
+    if (query.type == DataType::FLOAT) {
+      detail::cuda_check(cudaMemcpyAsync(p.query.ptr, static_cast<const void*>(query), q_bytes, cudaMemcpyHostToDevice, p.stream), "cudaMemcpyAsync(query)");
+    }
+    else {  // uint8: copy the bytes, widen on the device (exact)
+      p.stage.reserve(query.numel());
+      detail::cuda_check(cudaMemcpyAsync(p.stage.ptr, static_cast<const void*>(query), query.numel(), cudaMemcpyHostToDevice, p.stream), "cudaMemcpyAsync(query)");
+      detail::abi_check(ggnn_b200_widen_u8(static_cast<const uint8_t*>(p.stage.ptr), static_cast<float*>(p.query.ptr), query.numel(), p.stream));
+    }
+    KeyT* d_ids = static_cast<KeyT*>(p.ids.ptr);
+    ValueT* d_dists = static_cast<ValueT*>(p.dists.ptr);
+    for (uint32_t i = 0; i < s.spg; ++i) {
+      Shard& sh = s.shards[g.first_shard + i];
+      ggnn_b200_query_params qp = query_params(g.slots[sh.slot], dq, KQuery, tau_query, max_iterations, measure);
+      qp.d_query_results = d_ids;
+      qp.d_query_results_dists = d_dists;
+      qp.shards_per_gpu = s.spg;
+      qp.on_gpu_shard_id = i;
+      qp.d_work_counter = p.work_counter;
+      detail::abi_check(ggnn_b200_query(&qp, Nq, p.stream));
+    }
+    if (s.spg > 1) {  // replaces gpu_instance.cu:745-790
+      p.merged_ids.reserve(static_cast<size_t>(Nq) * KQuery * sizeof(KeyT));
+      p.merged_dists.reserve(static_cast<size_t>(Nq) * KQuery * sizeof(ValueT));
+      detail::abi_check(ggnn_b200_merge_topk(d_ids, d_dists, s.spg, KQuery, static_cast<size_t>(KQuery) * s.spg, KQuery, Nq, KQuery, 0,
+                                             static_cast<KeyT*>(p.merged_ids.ptr), static_cast<ValueT*>(p.merged_dists.ptr), p.stream));
+      d_ids = static_cast<KeyT*>(p.merged_ids.ptr);
+      d_dists = static_cast<ValueT*>(p.merged_dists.ptr);
+    }
+    QueryHandle h;
+    h.results.ids = Dataset<KeyT>::empty(Nq, KQuery, true);
+    h.results.dists = Dataset<ValueT>::empty(Nq, KQuery, true);
+    detail::cuda_check(cudaMemcpyAsync(h.results.ids.data(), d_ids, h.results.ids.size_bytes(), cudaMemcpyDeviceToHost, p.stream), "cudaMemcpyAsync(ids)");
+    detail::cuda_check(cudaMemcpyAsync(h.results.dists.data(), d_dists, h.results.dists.size_bytes(), cudaMemcpyDeviceToHost, p.stream), "cudaMemcpyAsync(dists)");
+    detail::cuda_check(cudaEventRecord(p.done, p.stream), "cudaEventRecord");
+    h.event = p.done;
+    return h;
   }
 
   [[nodiscard]] Results bfQuery(const GenericDataset& query, uint32_t KGT = 100, DistanceMeasure measure = DistanceMeasure::Euclidean)
   {
-    if (!base) throw std::runtime_error("The base needs to be set before running a brute-force query.");
-    if (gpu_ids.size() > 1) throw std::runtime_error("bfQuery supports only a single GPU.");  // ggnn.cu:338-339
+    State& s = *st;
+    if (!s.base) throw std::runtime_error("The base needs to be set before running a brute-force query.");
+    if (s.gpu_ids.size() > 1) throw std::runtime_error("bfQuery supports only a single GPU.");  // ggnn.cu:338-339
     check_query(query, "unsupported datatype for brute-force query");
-    const int gpu = gpu_ids[0];
+    const int gpu = s.gpu_ids[0];
     detail::DeviceGuard g(gpu);
     Dataset<float> b_dev;
     const float* db = nullptr;
-    if (shards.size() == 1) db = shards[0].base.data();
+    if (s.shards.size() == 1 && s.shards[0].slot >= 0) db = s.gpus[0].slots[s.shards[0].slot].base.data();
     else {
-      b_dev = float_on_gpu(*base, gpu, nullptr);
+      b_dev = float_on_gpu(*s.base, gpu, nullptr);
       db = b_dev.data();
     }
     Dataset<float> q_dev = float_on_gpu(query, gpu, nullptr);
@@ -733,32 +908,214 @@ class GGNN {
     out.ids = Dataset<KeyT>::emptyOnGPU(query.N, KGT, gpu);
     out.dists = Dataset<ValueT>::emptyOnGPU(query.N, KGT, gpu);
     ggnn_b200_bf_query_params p{};
-    p.D = base->D; p.measure = static_cast<int>(measure); p.KQuery = KGT; p.N_base = static_cast<int32_t>(base->N);
+    p.D = s.base->D; p.measure = static_cast<int>(measure); p.KQuery = KGT; p.N_base = static_cast<int32_t>(s.base->N);
     p.d_base = db; p.d_query = q_dev.data(); p.d_query_results = out.ids.data(); p.d_query_results_dists = out.dists.data();
-    p.workspace_bytes = ggnn_b200_bf_query_workspace_bytes(p.D, p.measure, KGT, static_cast<uint32_t>(base->N), static_cast<uint32_t>(query.N));
+    p.workspace_bytes = ggnn_b200_bf_query_workspace_bytes(p.D, p.measure, KGT, static_cast<uint32_t>(s.base->N), static_cast<uint32_t>(query.N));
     if (p.workspace_bytes) detail::cuda_check(cudaMalloc(&p.d_workspace, p.workspace_bytes), "cudaMalloc(bf workspace)");
     const int rc = ggnn_b200_bf_query(&p, static_cast<uint32_t>(query.N), nullptr);
     cudaDeviceSynchronize();
     if (p.d_workspace) cudaFree(p.d_workspace);
     detail::abi_check(rc);
-    return return_results_on_gpu ? std::move(out) : to_host(std::move(out));
+    return s.return_results_on_gpu ? std::move(out) : to_host(std::move(out));
   }
 
+  /// the graph of one shard on its GPU (swap mode: valid until the shard is swapped out)
   [[nodiscard]] const Graph& getGraph(uint32_t global_shard_id = 0)
   {
-    if (global_shard_id >= shards.size()) throw std::out_of_range("no such shard");
-    return shards[global_shard_id].graph;
+    State& s = *st;
+    if (global_shard_id >= s.shards.size()) throw std::out_of_range("no such shard");
+    Shard& sh = s.shards[global_shard_id];
+    Gpu& g = s.gpus[global_shard_id / s.spg];
+    detail::DeviceGuard guard(g.id);
+    Slot& slot = acquire(g, sh);
+    cudaStreamSynchronize(g.stream);
+    s.graph_view.config = s.cfg;
+    s.graph_view.offsets = s.off;
+    s.graph_view.memory = Dataset<uint8_t>{slot.blob.reference()};
+    return s.graph_view;
   }
 
  private:
-  struct Shard {
-    int gpu{0};
-    uint32_t global_id{0};
+  /// grow-only device buffer
+  struct DevBuf {
+    void* ptr{nullptr};
+    size_t cap{0};
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : ptr(o.ptr), cap(o.cap) { o.ptr = nullptr; o.cap = 0; }
+    ~DevBuf() { if (ptr) cudaFree(ptr); }
+    void reserve(size_t bytes)
+    {
+      if (bytes <= cap) return;
+      if (ptr) cudaFree(ptr);
+      ptr = nullptr;
+      cap = 0;
+      detail::cuda_check(cudaMalloc(&ptr, std::max<size_t>(bytes, 256)), "cudaMalloc(pipeline buffer)");
+      cap = bytes;
+    }
+  };
+  struct Pipe {
+    cudaStream_t stream{nullptr};
+    cudaEvent_t done{nullptr};
+    uint32_t* work_counter{nullptr};
+    DevBuf query, stage, ids, dists, merged_ids, merged_dists;
+  };
+  /// one (base rows, graph blob) buffer pair on a GPU
+  struct Slot {
     Dataset<float> base;
-    Graph graph;
+    Dataset<uint8_t> blob;
+    int64_t resident{-1};  // global shard id held, -1 = free
+    uint64_t last_use{0};
+  };
+  struct Shard {
+    uint32_t global_id{0};
+    int slot{-1};           // index into its GPU's slots, -1 = swapped out
+    bool has_graph{false}, dirty{false}, on_disk{false};
+    Dataset<uint8_t> host_blob;  // swapped-out graph in pinned host memory (else on disk / none yet)
+  };
+  struct Gpu {
+    int id{0};
+    uint32_t first_shard{0};
     cudaStream_t stream{nullptr};
     uint32_t* work_counter{nullptr};
+    void** d_gather_tbl{nullptr};
+    bool swap{false};
+    uint32_t query_calls{0};
+    uint64_t clock{0};
+    std::vector<Slot> slots;
+    std::vector<Pipe> pipes;
+    size_t next_pipe{0};
   };
+  struct State {
+    std::filesystem::path graph_dir{"."};
+    std::vector<int> gpu_ids{0};
+    uint32_t N_shard{0}, spg{1};
+    bool return_results_on_gpu{false};
+    bool peer_gather{false};
+    size_t cpu_memory_limit{std::numeric_limits<size_t>::max()}, reserved_gpu_memory{0};
+    size_t blob_bytes{0}, host_blobs{0};
+    GenericDataset owned_base{};
+    const GenericDataset* base{nullptr};
+    ggnn_b200_graph_config cfg{};
+    ggnn_b200_graph_offsets off{};
+    std::vector<Shard> shards;
+    std::vector<Gpu> gpus;
+    Graph graph_view;
+    ~State()
+    {
+      for (auto& g : gpus) {
+        cudaSetDevice(g.id);
+        cudaDeviceSynchronize();
+        for (auto& p : g.pipes) {
+          if (p.stream) cudaStreamDestroy(p.stream);
+          if (p.done) cudaEventDestroy(p.done);
+          if (p.work_counter) cudaFree(p.work_counter);
+        }
+        g.pipes.clear();
+        if (g.stream) cudaStreamDestroy(g.stream);
+        if (g.work_counter) cudaFree(g.work_counter);
+        if (g.d_gather_tbl) cudaFree(g.d_gather_tbl);
+      }
+    }
+  };
+  std::unique_ptr<State> st;
+
+  std::filesystem::path part_path(uint32_t global_id) const { return st->graph_dir / ("part_" + std::to_string(global_id) + ".ggnn"); }
+  static void write_file(const std::filesystem::path& path, const void* data, size_t bytes)
+  {
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    f.write(static_cast<const char*>(data), static_cast<std::streamsize>(bytes));
+    if (!f) throw std::runtime_error("cannot write " + path.string());
+  }
+  static void read_file(const std::filesystem::path& path, void* data, size_t bytes)
+  {
+    std::ifstream f(path, std::ios::binary);
+    f.read(static_cast<char*>(data), static_cast<std::streamsize>(bytes));
+    if (!f) throw std::runtime_error("cannot read " + path.string());
+  }
+  bool has_graph() const
+  {
+    if (st->shards.empty()) return false;
+    for (const auto& sh : st->shards)
+      if (!sh.has_graph) return false;
+    return true;
+  }
+
+  ggnn_b200_query_params query_params(const Slot& slot, const float* dq, uint32_t KQuery, float tau_query, uint32_t max_iterations,
+                                      DistanceMeasure measure) const
+  {
+    const State& s = *st;
+    const char* blob = reinterpret_cast<const char*>(slot.blob.data());
+    ggnn_b200_query_params p{};
+    p.D = s.cfg.D; p.measure = static_cast<int>(measure); p.KQuery = KQuery;
+    p.tau_query = tau_query; p.max_iterations = max_iterations;
+    p.N_base = static_cast<int32_t>(s.cfg.N); p.KBuild = s.cfg.KBuild; p.num_starting_points = s.cfg.S;
+    p.d_base = slot.base.data(); p.d_query = dq;
+    p.d_graph = reinterpret_cast<const KeyT*>(blob + s.off.graph);
+    p.d_starting_points = reinterpret_cast<const KeyT*>(blob + s.off.translation) + s.cfg.STs_offsets[GGNN_B200_L - 1];
+    p.d_nn1_stats = reinterpret_cast<const ValueT*>(blob + s.off.nn1_stats);
+    p.shards_per_gpu = 1;
+    return p;
+  }
+
+  /// the device buffers holding `sh` (current device = g.id).  Resident mode: its own slot.  Swap mode
+  /// (gpu_instance.cu:370-467 swapOutPart / swapInPart): the least recently used slot is written back -- graph blob to
+  /// pinned host memory up to the CPU memory limit, else to part_<id>.ggnn -- and refilled from the host base + graph;
+  /// everything is ordered on the GPU's one stream.
+  Slot& acquire(Gpu& g, Shard& sh)
+  {
+    State& s = *st;
+    if (sh.slot >= 0) {
+      g.slots[sh.slot].last_use = ++g.clock;
+      return g.slots[sh.slot];
+    }
+    size_t victim = 0;
+    for (size_t i = 0; i < g.slots.size(); ++i) {
+      if (g.slots[i].resident < 0) { victim = i; break; }
+      if (g.slots[i].last_use < g.slots[victim].last_use) victim = i;
+    }
+    Slot& slot = g.slots[victim];
+    detail::cuda_check(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");  // the victim's kernels are done
+    if (slot.resident >= 0) {
+      Shard& old = s.shards[static_cast<size_t>(slot.resident)];
+      if (old.dirty) {
+        if (!old.host_blob.data() && (s.host_blobs + 1) * s.blob_bytes <= s.cpu_memory_limit) {
+          old.host_blob = Dataset<uint8_t>::empty(s.blob_bytes, 1, true);
+          ++s.host_blobs;
+        }
+        if (old.host_blob.data()) {
+          detail::cuda_check(cudaMemcpy(old.host_blob.data(), slot.blob.data(), s.blob_bytes, cudaMemcpyDeviceToHost), "cudaMemcpy(swap out)");
+        }
+        else {
+          std::vector<uint8_t> h(s.blob_bytes);
+          detail::cuda_check(cudaMemcpy(h.data(), slot.blob.data(), s.blob_bytes, cudaMemcpyDeviceToHost), "cudaMemcpy(swap out)");
+          std::filesystem::create_directories(s.graph_dir);
+          write_file(part_path(old.global_id), h.data(), h.size());
+          old.on_disk = true;
+        }
+        old.dirty = false;
+      }
+      old.slot = -1;
+    }
+    // swap in: base rows from the host base, graph from host memory / disk (nothing yet before build)
+    const uint64_t n_shard = s.cfg.N;
+    Dataset<float> rows = float_on_gpu(*s.base, g.id, g.stream, static_cast<uint64_t>(sh.global_id) * n_shard, n_shard, &slot.base);
+    (void)rows;
+    if (sh.host_blob.data()) {
+      detail::cuda_check(cudaMemcpyAsync(slot.blob.data(), sh.host_blob.data(), s.blob_bytes, cudaMemcpyHostToDevice, g.stream), "cudaMemcpyAsync(swap in)");
+    }
+    else if (sh.on_disk) {
+      std::vector<uint8_t> h(s.blob_bytes);
+      read_file(part_path(sh.global_id), h.data(), h.size());
+      detail::cuda_check(cudaMemcpy(slot.blob.data(), h.data(), h.size(), cudaMemcpyHostToDevice), "cudaMemcpy(swap in)");
+    }
+    detail::cuda_check(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");
+    slot.resident = sh.global_id;
+    slot.last_use = ++g.clock;
+    sh.slot = static_cast<int>(victim);
+    return slot;
+  }
 
   static Results to_host(Results r)
   {
@@ -772,7 +1129,7 @@ class GGNN {
 
   void check_base(const GenericDataset& b) const
   {
-    if (!shards.empty()) throw std::runtime_error("The base cannot be changed after the graph has been set up.");
+    if (!st->shards.empty()) throw std::runtime_error("The base cannot be changed after the graph has been set up.");
     if (b.type != DataType::FLOAT && b.type != DataType::UINT8) throw std::runtime_error("unsupported datatype for base");  // ggnn.cu:456-491
     if (b.D < MIN_D || b.D > MAX_D) throw std::out_of_range("unsupported dimension");
   }
@@ -780,25 +1137,30 @@ class GGNN {
   {
     if (q.type != DataType::FLOAT && q.type != DataType::UINT8) throw std::runtime_error(what);
     // the reference CHECK-aborts here (ggnn.cu:524-540)
-    if (q.type != base->type) throw std::runtime_error("query data type does not match base data type");
-    if (q.D != base->D) throw std::out_of_range("query dimension does not match the base");
+    if (q.type != st->base->type) throw std::runtime_error("query data type does not match base data type");
+    if (q.D != st->base->D) throw std::out_of_range("query dimension does not match the base");
   }
 
   /// rows [from, from + num) of `src` (float or uint8, anywhere) as fp32 on `gpu`; uint8 is widened on the device.
-  /// Already-resident float data is referenced, not copied.  The current device must be `gpu`.
+  /// Already-resident float data is referenced, not copied -- unless `into` names the buffer to fill (swap slots).
+  /// The current device must be `gpu`.
   static Dataset<float> float_on_gpu(const GenericDataset& src, int gpu, cudaStream_t stream, uint64_t from = 0,
-                                     uint64_t num = std::numeric_limits<uint64_t>::max())
+                                     uint64_t num = std::numeric_limits<uint64_t>::max(), Dataset<float>* into = nullptr)
   {
     if (num == std::numeric_limits<uint64_t>::max()) num = src.N - from;
     GenericDataset rows = src.referenceRange(from, num);
     const bool resident = rows.isGPUAccessible() && (rows.gpu_id == gpu || rows.location == DataLocation::MANAGED);
+    auto target = [&]() {
+      if (into) return Dataset<float>{into->referenceRange(0, num)};
+      return Dataset<float>::emptyOnGPU(num, src.D, gpu);
+    };
     if (rows.type == DataType::FLOAT) {
-      if (resident) return Dataset<float>{std::move(rows)};
-      Dataset<float> d = Dataset<float>::emptyOnGPU(num, src.D, gpu);
+      if (resident && !into) return Dataset<float>{std::move(rows)};
+      Dataset<float> d = target();
       detail::cuda_check(cudaMemcpyAsync(d.data(), static_cast<const void*>(rows), rows.required_size_bytes(), cudaMemcpyDefault, stream), "cudaMemcpyAsync(float rows)");
       return d;
     }
-    Dataset<float> d = Dataset<float>::emptyOnGPU(num, src.D, gpu);
+    Dataset<float> d = target();
     Dataset<uint8_t> staged;
     const uint8_t* u8 = static_cast<const uint8_t*>(static_cast<const void*>(rows));
     if (!resident) {
@@ -811,50 +1173,79 @@ class GGNN {
     return d;
   }
 
-  // src/ggnn/base/ggnn.cu:154-203
+  // src/ggnn/base/ggnn.cu:154-203 (partitioning), gpu_instance.cu:135-227 (how many shards fit on a GPU)
   void prepare(uint32_t KBuild)
   {
-    if (!base || !static_cast<const void*>(*base)) throw std::runtime_error("The base needs to be set before building a graph.");
+    State& s = *st;
+    if (!s.base || !static_cast<const void*>(*s.base)) throw std::runtime_error("The base needs to be set before building a graph.");
     if (KBuild < MIN_KBUILD || KBuild > MAX_KBUILD) throw std::out_of_range("KBuild out of range");
-    if (!shards.empty()) {
-      if (cfg.KBuild != KBuild) throw std::runtime_error("graph already set up with a different KBuild");
+    if (!s.shards.empty()) {
+      if (s.cfg.KBuild != KBuild) throw std::runtime_error("graph already set up with a different KBuild");
       return;
     }
-    const uint64_t N = base->N;
-    const uint64_t n_shard = N_shard ? N_shard : N;
+    const uint64_t N = s.base->N;
+    const uint64_t n_shard = s.N_shard ? s.N_shard : N;
     if (N % n_shard) throw std::out_of_range("The base size needs to be divisible by the shard size.");
     const uint64_t num_shards = N / n_shard;
-    if (num_shards % gpu_ids.size()) throw std::out_of_range("The number of shards needs to be divisible by the number of GPUs.");
-    spg = static_cast<uint32_t>(num_shards / gpu_ids.size());
-    detail::abi_check(ggnn_b200_graph_config_init(&cfg, static_cast<uint32_t>(n_shard), base->D, KBuild));
-    ggnn_b200_graph_offsets off;
-    ggnn_b200_graph_blob_offsets(&cfg, &off);
-    shards.resize(num_shards);
-    for (uint32_t gi = 0; gi < gpu_ids.size(); ++gi) {
-      detail::DeviceGuard g(gpu_ids[gi]);
-      for (uint32_t s = 0; s < spg; ++s) {
-        Shard& sh = shards[gi * spg + s];
-        sh.gpu = gpu_ids[gi];
-        sh.global_id = gi * spg + s;
-        detail::cuda_check(cudaStreamCreate(&sh.stream), "cudaStreamCreate");
-        detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&sh.work_counter), 16), "cudaMalloc");
-        sh.base = float_on_gpu(*base, sh.gpu, sh.stream, static_cast<uint64_t>(sh.global_id) * n_shard, n_shard);
-        sh.graph.config = cfg;
-        sh.graph.offsets = off;
-        sh.graph.memory = Dataset<uint8_t>::emptyOnGPU(off.total, 1, sh.gpu);
-        detail::cuda_check(cudaStreamSynchronize(sh.stream), "cudaStreamSynchronize");
+    if (num_shards % s.gpu_ids.size()) throw std::out_of_range("The number of shards needs to be divisible by the number of GPUs.");
+    s.spg = static_cast<uint32_t>(num_shards / s.gpu_ids.size());
+    detail::abi_check(ggnn_b200_graph_config_init(&s.cfg, static_cast<uint32_t>(n_shard), s.base->D, KBuild));
+    ggnn_b200_graph_blob_offsets(&s.cfg, &s.off);
+    s.blob_bytes = s.off.total;
+    const size_t shard_bytes = n_shard * s.base->D * sizeof(float) + s.blob_bytes;
+    const size_t scratch_bytes = ggnn_b200_build_scratch_bytes(&s.cfg);
+    s.shards.resize(num_shards);
+    s.gpus.resize(s.gpu_ids.size());
+    for (uint32_t gi = 0; gi < s.gpu_ids.size(); ++gi) {
+      Gpu& g = s.gpus[gi];
+      g.id = s.gpu_ids[gi];
+      g.first_shard = gi * s.spg;
+      detail::DeviceGuard guard(g.id);
+      detail::cuda_check(cudaStreamCreate(&g.stream), "cudaStreamCreate");
+      detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&g.work_counter), 16), "cudaMalloc");
+      detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&g.d_gather_tbl), 16), "cudaMalloc");
+      // a base that already lives on this GPU stays there (referenced, never swapped)
+      const bool base_on_gpu = s.base->isGPUAccessible() && s.base->type == DataType::FLOAT &&
+                               (s.base->gpu_id == g.id || s.base->location == DataLocation::MANAGED);
+      uint32_t n_buf = s.spg;
+      if (!base_on_gpu) {
+        size_t free_b = 0, total_b = 0;
+        detail::cuda_check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+        const size_t need = s.reserved_gpu_memory + scratch_bytes;
+        const size_t fit = free_b > need ? (free_b - need) / shard_bytes : 0;
+        if (const char* e = std::getenv("GGNN_B200_GPU_SHARD_BUFFERS"); e && std::atoi(e) > 0) n_buf = std::min<uint32_t>(s.spg, std::atoi(e));
+        else n_buf = static_cast<uint32_t>(std::min<size_t>(s.spg, fit));
+        if (n_buf < 1) throw std::runtime_error("not enough GPU memory for a single shard (base + graph + build scratch); use a smaller shard size");
+      }
+      g.swap = n_buf < s.spg;
+      g.slots.resize(n_buf);
+      for (uint32_t b = 0; b < n_buf; ++b) {
+        Slot& slot = g.slots[b];
+        slot.blob = Dataset<uint8_t>::emptyOnGPU(s.blob_bytes, 1, g.id);
+        if (g.swap) slot.base = Dataset<float>::emptyOnGPU(n_shard, s.base->D, g.id);
+      }
+      for (uint32_t i = 0; i < s.spg; ++i) {
+        Shard& sh = s.shards[g.first_shard + i];
+        sh.global_id = g.first_shard + i;
+        if (!g.swap) {  // resident: shard i <-> slot i for good
+          Slot& slot = g.slots[i];
+          slot.base = float_on_gpu(*s.base, g.id, g.stream, static_cast<uint64_t>(sh.global_id) * n_shard, n_shard);
+          slot.resident = sh.global_id;
+          sh.slot = static_cast<int>(i);
+        }
+      }
+      detail::cuda_check(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");
+    }
+    // several GPUs: can they all store into the first one's memory?  (fused shard-merge exchange)
+    s.peer_gather = false;
+    if (s.gpus.size() > 1 && !std::getenv("GGNN_B200_NO_PEER_GATHER")) {
+      s.peer_gather = true;
+      for (size_t gi = 1; gi < s.gpus.size(); ++gi) {
+        detail::DeviceGuard guard(s.gpus[gi].id);
+        if (ggnn_b200_peer_enable(s.gpus[0].id) != 0) s.peer_gather = false;
       }
     }
   }
-
-  std::filesystem::path graph_dir{"."};
-  std::vector<int> gpu_ids{0};
-  uint32_t N_shard{0}, spg{1};
-  bool return_results_on_gpu{false};
-  GenericDataset owned_base{};
-  const GenericDataset* base{nullptr};
-  ggnn_b200_graph_config cfg{};
-  std::vector<Shard> shards;
 };
 
 }  // namespace ggnn

@@ -98,6 +98,19 @@ typedef struct {
   uint32_t on_gpu_shard_id;
   uint32_t* d_work_counter;         /* optional device uint32 used for dynamic query scheduling
                                        (zeroed by the call on `stream`); NULL = static mapping */
+  /* --- fused shard-merge exchange (optional; all zero = off).  Replaces the D2H copy + CPU heap merge of
+   * src/ggnn/base/result_merger.cpp:51-149 / gpu_instance.cu:714-742: the kernel's epilogue stores each query's
+   * KQuery (id, dist) pairs straight into the gathered buffer of every destination GPU (peer-mapped memory: NVLink
+   * stores), and the last warp of the launch bumps a flag word in every destination.  A destination buffer holds
+   * ids [n_slots][scatter_rows][KQuery] int32 and, scatter_dists_offset bytes further, dists of the same shape;
+   * this launch writes list `scatter_slot` with shard-local ids (no id offset).  d_query_results may be NULL then. */
+  uint32_t n_scatter;               /* number of destination buffers */
+  uint32_t scatter_slot;
+  uint32_t scatter_rows;            /* >= N_query */
+  size_t scatter_dists_offset;
+  void* const* d_scatter_dst;       /* device array [n_scatter] of destination buffer base pointers */
+  uint32_t* const* d_scatter_flags; /* device array [n_scatter] of flag words (one per destination), or NULL */
+  uint32_t* d_scatter_done;         /* local device word, zero before the first use (reset by every launch) */
 } ggnn_b200_query_params;
 
 int ggnn_b200_query(const ggnn_b200_query_params* p, uint32_t N_query, ggnn_b200_stream_t stream);
@@ -173,6 +186,23 @@ int ggnn_b200_merge_topk(const int32_t* d_ids, const float* d_dists, uint32_t n_
                          size_t query_stride, uint32_t K_in, uint32_t N_query, uint32_t K,
                          int64_t id_offset_per_list, int32_t* d_out_ids, float* d_out_dists,
                          ggnn_b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Peer-memory plumbing of the fused shard-merge exchange (one process per GPU: CUDA IPC; one process with several
+ * GPUs: peer access).  The reference has no device-side exchange (per-GPU D2H + CPU merge, gpu_instance.cu:714-742).
+ * ggnn_b200_ipc_alloc: cudaMalloc + zero fill + cudaIpcGetMemHandle (handle = 64 bytes, to be sent to the peers);
+ * ggnn_b200_ipc_open / _close: map / unmap a peer's allocation in this process; ggnn_b200_ipc_free: cudaFree.
+ * ggnn_b200_peer_enable: cudaDeviceEnablePeerAccess(peer) for the current device (already enabled = success).
+ * ggnn_b200_wait_flag: stream-ordered wait until *d_flag >= expected (one polling thread, no SM time to speak of);
+ * after timeout_ms (0 = 10 s) it gives up, stores 1 to *d_timed_out (may be NULL) and lets the stream continue.
+ * ---------------------------------------------------------------------------------------------- */
+int ggnn_b200_ipc_alloc(size_t bytes, void** d_ptr, unsigned char* handle64);
+int ggnn_b200_ipc_open(const unsigned char* handle64, void** d_ptr);
+int ggnn_b200_ipc_close(void* d_ptr);
+int ggnn_b200_ipc_free(void* d_ptr);
+int ggnn_b200_peer_enable(int peer_device);
+int ggnn_b200_wait_flag(const uint32_t* d_flag, uint32_t expected, uint32_t timeout_ms, uint32_t* d_timed_out,
+                        ggnn_b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * uint8 base / query vectors (the reference's BaseT = uint8_t instantiation, include/ggnn/base/lib.h:26-28).

@@ -1,0 +1,121 @@
+// host_paths_test -- GPU test of the C++ host API paths that the reference's example programs do not reach
+// (include/ggnn/ggnn.hpp): shard swapping GPU <-> host <-> disk (setCPUMemoryLimit / GGNN_B200_GPU_SHARD_BUFFERS,
+// reference gpu_instance.cu:135-227, 370-467), several GPUs with the lists gathered by peer stores and results left on
+// the GPU, queryAsync with batches in flight, moving a GGNN object.  Every variant must return exactly the results of
+// the plain all-resident single-GPU run on the same stored graphs.   usage: host_paths_test <workdir>
+#include <ggnn/base/ggnn.cuh>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace ggnn;
+
+static bool same(const GGNN<int32_t, float>::Results& a, const GGNN<int32_t, float>::Results& b)
+{
+  return a.ids.size() == b.ids.size() && !std::memcmp(a.ids.data(), b.ids.data(), a.ids.size_bytes()) &&
+         !std::memcmp(a.dists.data(), b.dists.data(), a.dists.size_bytes());
+}
+
+int main(int argc, char** argv)
+{
+  const std::string dir = argc > 1 ? argv[1] : "/tmp/ggnn_host_paths";
+  const size_t N = 40000, Nq = 3000;
+  const uint32_t D = 64, K = 10, n_shard = 10000;
+  std::vector<float> bv(N * D), qv(Nq * D);
+  std::mt19937 prng{7};
+  std::uniform_real_distribution<float> uni{0.f, 1.f};
+  for (float& x : bv) x = uni(prng);
+  for (float& x : qv) x = uni(prng);
+  Dataset<float> base = Dataset<float>::copy(bv, D, true);
+  Dataset<float> query = Dataset<float>::copy(qv, D, true);
+  int failures = 0;
+  auto check = [&](bool ok, const char* what) {
+    std::printf("%s: %s\n", what, ok ? "ok" : "FAILED");
+    failures += !ok;
+  };
+
+  unsetenv("GGNN_B200_GPU_SHARD_BUFFERS");
+  GGNN<int32_t, float> a{};
+  a.setWorkingDirectory(dir);
+  a.setShardSize(n_shard);
+  a.setBaseReference(base);
+  a.build(24, 0.5f);
+  a.store();
+  const auto ref = a.query(query, K, 0.64f, 400);
+
+  {  // moved object keeps working (its base pointer must not dangle)
+    GGNN<int32_t, float> tmp{};
+    tmp.setWorkingDirectory(dir);
+    tmp.setShardSize(n_shard);
+    tmp.setBase(Dataset<float>::copy(bv, D, false));
+    tmp.load(24);
+    GGNN<int32_t, float> moved = std::move(tmp);
+    check(same(moved.query(query, K, 0.64f, 400), ref), "moved GGNN");
+    bool threw = false;
+    GGNN<int32_t, float> empty{};
+    try { empty.store(); } catch (const std::runtime_error&) { threw = true; }
+    check(threw, "store() without a graph throws");
+  }
+  {  // queryAsync: three batches in flight
+    auto h1 = a.queryAsync(query, K, 0.64f, 400);
+    auto h2 = a.queryAsync(query, K, 0.64f, 400);
+    auto h3 = a.queryAsync(query, K, 0.64f, 400);
+    check(same(h1.get(), ref) && same(h2.get(), ref) && same(h3.get(), ref), "queryAsync x3");
+  }
+  for (const char* buffers : {"2", "1"}) {  // swap mode: 2 then 1 device buffers for 4 shards; graphs in host memory / on disk
+    setenv("GGNN_B200_GPU_SHARD_BUFFERS", buffers, 1);
+    GGNN<int32_t, float> s{};
+    s.setWorkingDirectory(dir);
+    s.setShardSize(n_shard);
+    s.setCPUMemoryLimit(buffers[0] == '1' ? 0 : size_t(1) << 30);
+    s.setBaseReference(base);
+    s.load(24);
+    const bool ok1 = same(s.query(query, K, 0.64f, 400), ref);
+    const bool ok2 = same(s.query(query, K, 0.64f, 400), ref);  // opposite shard order
+    check(ok1 && ok2, (std::string("swap, device buffers = ") + buffers).c_str());
+  }
+  {  // swap mode build: graphs differ (construction is not deterministic), so only sanity: recall vs brute force
+    setenv("GGNN_B200_GPU_SHARD_BUFFERS", "1", 1);
+    GGNN<int32_t, float> s{};
+    s.setWorkingDirectory(dir + "/swapbuild");
+    s.setShardSize(n_shard);
+    s.setCPUMemoryLimit(200000);  // room for nothing: graphs go to disk
+    s.setBaseReference(base);
+    s.build(24, 0.5f);
+    const auto r = s.query(query, K, 0.64f, 400);
+    unsetenv("GGNN_B200_GPU_SHARD_BUFFERS");
+    const auto gt = a.bfQuery(query, K);
+    size_t hits = 0;
+    for (size_t n = 0; n < Nq; ++n)
+      for (uint32_t i = 0; i < K; ++i)
+        for (uint32_t j = 0; j < K; ++j) hits += r.ids[n * K + i] == gt.ids[n * K + j];
+    check(hits > Nq * K * 8 / 10, "swap-mode build recall");
+  }
+  unsetenv("GGNN_B200_GPU_SHARD_BUFFERS");
+  {  // two "GPUs" (device 0 twice on a one-GPU box, devices 0 and 1 otherwise): peer gather, results may stay on the GPU
+    int n_dev = 0;
+    cudaGetDeviceCount(&n_dev);
+    for (int no_gather = 0; no_gather < 2; ++no_gather) {
+      if (no_gather) setenv("GGNN_B200_NO_PEER_GATHER", "1", 1);
+      GGNN<int32_t, float> m{};
+      m.setWorkingDirectory(dir);
+      m.setGPUs({0, n_dev > 1 ? 1 : 0});
+      m.setShardSize(n_shard);
+      m.setBaseReference(base);
+      m.load(24);
+      check(same(m.query(query, K, 0.64f, 400), ref), no_gather ? "2 GPUs, peer copies" : "2 GPUs, peer-store gather");
+      m.setReturnResultsOnGPU(true);
+      auto on_gpu = m.query(query, K, 0.64f, 400);
+      std::vector<int32_t> h(Nq * K);
+      cudaMemcpy(h.data(), on_gpu.ids.data(), h.size() * 4, cudaMemcpyDeviceToHost);
+      check(on_gpu.ids.isGPUAccessible() && !std::memcmp(h.data(), ref.ids.data(), h.size() * 4), "2 GPUs, results on the GPU");
+      unsetenv("GGNN_B200_NO_PEER_GATHER");
+    }
+  }
+  std::printf("%s\n", failures ? "FAILED" : "ALL OK");
+  return failures ? 1 : 0;
+}
