@@ -403,6 +403,7 @@ def run_ours(a):
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) * 1e3, r
     e2e_sync_ms, r_sync = timed_host(e2e_sync, a.steps)
+    r_sync = tuple(t.clone() for t in r_sync)   # (N > 1: the pinned result buffers are reused by the next run)
     e2e_ms, e2e_depth = e2e_sync_ms, 1
     if depth > 1 and (world == 1 or n_streams > 1):
         e2e_ms, r_async = timed_host(e2e_async, a.steps)

@@ -80,6 +80,33 @@ __device__ __forceinline__ void tma_gather4(void* smem_dst, const void* tmap, in
       : "memory");
 }
 
+// the same on 32-bit shared-memory addresses computed once per warp (no generic -> shared conversion per call)
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar_s, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity)
+{
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_s), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_gather4_s(uint32_t dst_s, const void* tmap, int r0, int r1, int r2, int r3, uint32_t bar_s)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          dst_s),
+      "l"(tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar_s)
+      : "memory");
+}
+
 // 16-byte asynchronous copy global -> shared (SASS: LDGSTS.E.BYPASS.128), one warp instruction moves a
 // whole 512-byte row; used as the alternative row-staging mode (see traverse.cuh)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
@@ -297,7 +324,24 @@ struct WarpLists {
   float dist[NS];
   uint32_t head;  // physical prioQ head (uniform)
   uint32_t BEST;  // uniform
+  // per-lane slot predicates of push(), which only change when the head moves (pop / transform): for register j,
+  // bit 3j = slot p may take over its predecessor's entry (p >= 1, p != BEST, p != head), bit 3j+1 = slot p has a
+  // predecessor to compare with (p != 0, p != head), bit 3j+2 = p == BEST
+  uint32_t lane_flags;
   static constexpr uint32_t SORTED = 32u * NS;
+
+  __device__ __forceinline__ void update_flags()
+  {
+    uint32_t f = 0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const uint32_t p = 32u * j + lane_id();
+      f |= ((p >= 1) && (p != BEST) && (p != head)) ? (1u << (3 * j)) : 0u;
+      f |= ((p != 0) && (p != head)) ? (2u << (3 * j)) : 0u;
+      f |= (p == BEST) ? (4u << (3 * j)) : 0u;
+    }
+    lane_flags = f;
+  }
 
   __device__ __forceinline__ void init(uint32_t best)
   {
@@ -308,6 +352,7 @@ struct WarpLists {
       key[j] = EMPTY_KEY;
       dist[j] = G200_INF;
     }
+    update_flags();
   }
   // common interface with SmemLists (the lists live in registers: no backing store needed)
   __device__ __forceinline__ void init(uint32_t best, void*, uint32_t) { init(best); }
@@ -342,19 +387,22 @@ struct WarpLists {
 
   // simple_knn_cache.cuh:126-213 -- all slots updated at once (see DESIGN.md for the equivalence
   // with the reference's block-by-block loop)
-  __device__ __forceinline__ void push(int k, float d)
+  // check_dup (uniform): false when the caller knows that k is not in the lists (a candidate that passed the fetch
+  // filter and is no duplicate within its fetch: nothing but other candidates of that fetch has been pushed since)
+  __device__ __forceinline__ void push(int k, float d, bool check_dup = true)
   {
     const int lane = lane_id();
-    bool dup = false;
+    if (check_dup) {
+      bool dup = false;
 #pragma unroll
-    for (int j = 0; j < NS; ++j) dup |= (key[j] == k);
-    if (__any_sync(FULL, dup)) return;  // :132-146
+      for (int j = 0; j < NS; ++j) dup |= (key[j] == k);
+      if (__any_sync(FULL, dup)) return;  // :132-146
+    }
 
     int nk[NS];
     float asd[NS];
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      const uint32_t p = 32u * j + lane;
       int pk = __shfl_up_sync(FULL, key[j], 1);
       float pd = __shfl_up_sync(FULL, dist[j], 1);
       if (j > 0) {
@@ -367,22 +415,21 @@ struct WarpLists {
       }
       // slot p receives old[p-1] iff p-1 is active and non-empty and p is neither the start of the
       // best list / prioQ region nor the ring head (:166-172; idx_next==BEST swallows the ring wrap)
-      const bool recv = (p >= 1) && (p != BEST) && (p != head) && (pd >= d) && (pk != EMPTY_KEY);
+      const bool recv = ((lane_flags >> (3 * j)) & 1u) && (pd >= d) && (pk != EMPTY_KEY);
       asd[j] = recv ? pd : dist[j];
       nk[j] = recv ? pk : key[j];
     }
     const float last_asd = __shfl_sync(FULL, asd[NS - 1], 31);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-      const uint32_t p = 32u * j + lane;
       float pa = __shfl_up_sync(FULL, asd[j], 1);
       if (j > 0) {
         const float ca = __shfl_sync(FULL, asd[j - 1], 31);
         if (lane == 0) pa = ca;
       }
-      if (p == BEST) pa = last_asd;  // idx_prev = SORTED-1 (:177)
+      if ((lane_flags >> (3 * j)) & 4u) pa = last_asd;  // p == BEST: idx_prev = SORTED-1 (:177)
       const bool active = dist[j] >= d;
-      const bool has_prev = (p != 0) && (p != head);
+      const bool has_prev = (lane_flags >> (3 * j)) & 2u;
       const bool ins = active && (!has_prev || pa < d);  // :176-182
       key[j] = ins ? k : nk[j];
       dist[j] = ins ? d : asd[j];
@@ -404,6 +451,7 @@ struct WarpLists {
       }
     }
     head = (head + 1 >= SORTED) ? BEST : head + 1;
+    update_flags();
     return k;
   }
 
@@ -457,12 +505,14 @@ struct SmemLists {
   __device__ __forceinline__ float dist_at(uint32_t p) const { return dist[p]; }
   __device__ __forceinline__ int key_at(uint32_t p) const { return key[p]; }
 
-  __device__ __forceinline__ void push(int k, float d)
+  __device__ __forceinline__ void push(int k, float d, bool check_dup = true)
   {
     const int lane = lane_id();
-    bool dup = false;
-    for (uint32_t p = lane; p < SORTED; p += 32) dup |= (key[p] == k);
-    if (__any_sync(FULL, dup)) return;  // :132-146
+    if (check_dup) {
+      bool dup = false;
+      for (uint32_t p = lane; p < SORTED; p += 32) dup |= (key[p] == k);
+      if (__any_sync(FULL, dup)) return;  // :132-146
+    }
 
     // asd[SORTED-1] is what slot BEST compares against (idx_prev = SORTED-1, :177)
     const float od_l1 = dist[SORTED - 1], od_l2 = dist[SORTED - 2];

@@ -405,6 +405,7 @@ __device__ __forceinline__ void lists_transform(WarpLists<NS>& L, const int32_t*
     L.dist[j] = nd[j];
   }
   L.head = BEST;
+  L.update_flags();
 }
 
 template <int NS, bool FAST, int D32, int NW, bool G4 = false>

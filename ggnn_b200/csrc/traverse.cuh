@@ -322,23 +322,24 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
     const int m2 = __shfl_down_sync(FULL, mp, 2);
     const int m3 = __shfl_down_sync(FULL, mp, 3);
     const bool issuer = ((lane & 3) == 0) && lane < cnt;
-    float* const dst = ws.stage + (lane & 15) * D;
-    uint64_t* const my_bar = &ws.bar[(lane >> 3) & 1];
+    const uint32_t bar_s = smem_u32(ws.bar);  // bar[0], bar[1] at bar_s, bar_s + 8
+    const uint32_t dst_s = smem_u32(ws.stage) + static_cast<uint32_t>(lane & 15) * (D * 4u);
+    const uint32_t my_bar_s = bar_s + 8u * ((lane >> 3) & 1);
     if (lane == 0) {
-      mbar_expect_tx(&ws.bar[0], static_cast<uint32_t>(min(2, nquads)) * QUAD_BYTES);
-      if (nquads > 2) mbar_expect_tx(&ws.bar[1], static_cast<uint32_t>(min(2, nquads - 2)) * QUAD_BYTES);
+      mbar_expect_tx_s(bar_s, static_cast<uint32_t>(min(2, nquads)) * QUAD_BYTES);
+      if (nquads > 2) mbar_expect_tx_s(bar_s + 8u, static_cast<uint32_t>(min(2, nquads - 2)) * QUAD_BYTES);
     }
-    if (issuer && lane < 16) tma_gather4(dst, ws.tmap, m, m1, m2, m3, my_bar);
+    if (issuer && lane < 16) tma_gather4_s(dst_s, ws.tmap, m, m1, m2, m3, my_bar_s);
     for (int g = 0; g < ngroups; ++g) {
       const int buf = g & 1;
-      mbar_wait(&ws.bar[buf], (ws.parity >> buf) & 1u);
+      mbar_wait_s(bar_s + 8u * buf, (ws.parity >> buf) & 1u);
       ws.parity ^= 1u << buf;
       const float dg = dist8_fast<D32, NW>(ws.stage + buf * 8 * D, min(8, cnt - 8 * g), qv.cfg.measure, qv.q, qv.q_norm);
       if ((lane >> 3) == g) mine = dg;
       __syncwarp();  // the group's rows have been read: its buffer may be refilled
       if (g + 2 < ngroups) {
-        if (lane == 0) mbar_expect_tx(&ws.bar[buf], static_cast<uint32_t>(min(2, nquads - 2 * (g + 2))) * QUAD_BYTES);
-        if (issuer && (lane >> 3) == g + 2) tma_gather4(dst, ws.tmap, m, m1, m2, m3, my_bar);
+        if (lane == 0) mbar_expect_tx_s(bar_s + 8u * buf, static_cast<uint32_t>(min(2, nquads - 2 * (g + 2))) * QUAD_BYTES);
+        if (issuer && (lane >> 3) == g + 2) tma_gather4_s(dst_s, ws.tmap, m, m1, m2, m3, my_bar_s);
       }
     }
   }
@@ -377,8 +378,17 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
     }
   }
 
+  // duplicates WITHIN this fetch (a graph row may name a point twice): only those can already be in the lists when
+  // their turn comes -- every other candidate passed the filter and nothing but its fellow candidates is pushed before it
+  unsigned dupmask = FULL;
+  if constexpr (FILTER) {
+    const unsigned same = __match_any_sync(FULL, lane < cnt ? key_r : (-2 - lane));
+    dupmask = __ballot_sync(FULL, (same & ((1u << lane) - 1u)) != 0u);
+  }
+  float best_last = L.dist_at(L.BEST - 1);  // criteria() = best_last + xi (simple_knn_cache.cuh:284)
+
   if (pf_graph) {
-    const float crit0 = L.dist_at(L.BEST - 1) + xi;
+    const float crit0 = best_last + xi;
     const bool pass = lane < cnt && mine < crit0;
     if (spec && pf_stride <= 32) {
       // predicted next anchor = min(current prioQ head, best passing candidate); distances are >= 0, so their bit
@@ -403,17 +413,19 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
     }
   }
 
-  // pushes in candidate order; criteria re-evaluated after each push
-  unsigned rem = cnt >= 32 ? FULL : ((1u << cnt) - 1u);
-  while (true) {
-    const float crit = L.dist_at(L.BEST - 1) + xi;
-    const unsigned pm = __ballot_sync(FULL, mine < crit) & rem;
-    if (!pm) break;
+  // pushes in candidate order; criteria() is re-read after each push (:284) -- it only changes when the push changed the
+  // last entry of the best list, i.e. when d < best_last (it never grows, so the pending mask only loses bits)
+  unsigned pm = __ballot_sync(FULL, mine < best_last + xi) & (cnt >= 32 ? FULL : ((1u << cnt) - 1u));
+  while (pm) {
     const int c0 = __ffs(pm) - 1;
     const int k = __shfl_sync(FULL, key_r, c0);
     const float d = __shfl_sync(FULL, mine, c0);
-    L.push(k, d);
-    rem &= ~((2u << c0) - 1u);
+    L.push(k, d, (dupmask >> c0) & 1u);
+    pm &= pm - 1u;
+    if (d < best_last) {
+      best_last = L.dist_at(L.BEST - 1);
+      pm &= __ballot_sync(FULL, mine < best_last + xi);
+    }
   }
 }
 

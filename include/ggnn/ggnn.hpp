@@ -28,10 +28,12 @@
 #include <fstream>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <ostream>
 #include <span>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -94,6 +96,47 @@ inline void abi_check(int rc)
   if (rc == GGNN_B200_ERR_INVALID) throw std::out_of_range(msg);
   throw std::runtime_error(msg);
 }
+/// Recycles pinned host buffers (results of query() / bfQuery()): cudaMallocHost / cudaFreeHost cost more than a whole
+/// query batch on a B200 (milliseconds: page pinning + mapping into every device), so freed buffers of up to 64 MB are kept
+/// (at most 256 MB in total) and handed out again for the same size.
+class PinnedPool {
+ public:
+  static PinnedPool& instance()
+  {
+    static PinnedPool pool;
+    return pool;
+  }
+  void* get(size_t bytes)
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = free_.find(bytes);
+    if (it == free_.end()) return nullptr;
+    void* p = it->second;
+    free_.erase(it);
+    held -= bytes;
+    return p;
+  }
+  bool put(void* p, size_t bytes)
+  {
+    if (bytes > MAX_BUFFER) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (held + bytes > MAX_HELD) return false;
+    free_.emplace(bytes, p);
+    held += bytes;
+    return true;
+  }
+  ~PinnedPool()
+  {
+    for (auto& kv : free_) cudaFreeHost(kv.second);  // (errors at process teardown are of no interest)
+  }
+
+ private:
+  static constexpr size_t MAX_BUFFER = size_t(64) << 20, MAX_HELD = size_t(256) << 20;
+  std::mutex mu;
+  std::unordered_multimap<size_t, void*> free_;
+  size_t held{0};
+};
+
 struct DeviceGuard {
   int prev{0};
   explicit DeviceGuard(int dev)
@@ -203,7 +246,11 @@ struct GenericDataset {
         detail::cuda_check(cudaMalloc(&d.mem, bytes), "cudaMalloc");
         break;
       }
-      case DataLocation::CPU_PINNED: detail::cuda_check(cudaMallocHost(&d.mem, bytes), "cudaMallocHost"); break;
+      case DataLocation::CPU_PINNED:
+        d.alloc_bytes = (bytes + 255) / 256 * 256;
+        d.mem = detail::PinnedPool::instance().get(d.alloc_bytes);
+        if (!d.mem) detail::cuda_check(cudaMallocHost(&d.mem, d.alloc_bytes), "cudaMallocHost");
+        break;
       case DataLocation::CPU_MALLOC:
         d.mem = std::malloc(bytes);
         if (!d.mem) throw std::bad_alloc();
@@ -228,6 +275,7 @@ struct GenericDataset {
 
  protected:
   void* mem{nullptr};
+  size_t alloc_bytes{0};  // pinned allocations: the size the buffer was obtained with (pool key)
 
   template <typename T>
   void check_type() const
@@ -236,8 +284,8 @@ struct GenericDataset {
   }
   void take(GenericDataset& o) noexcept
   {
-    N = o.N; D = o.D; type = o.type; location = o.location; gpu_id = o.gpu_id; mem = o.mem;
-    o.mem = nullptr; o.N = 0; o.location = DataLocation::UNKNOWN;
+    N = o.N; D = o.D; type = o.type; location = o.location; gpu_id = o.gpu_id; mem = o.mem; alloc_bytes = o.alloc_bytes;
+    o.mem = nullptr; o.N = 0; o.location = DataLocation::UNKNOWN; o.alloc_bytes = 0;
   }
   void release() noexcept
   {
@@ -245,7 +293,9 @@ struct GenericDataset {
     switch (location) {
       case DataLocation::GPU:
       case DataLocation::MANAGED: cudaFree(mem); break;
-      case DataLocation::CPU_PINNED: cudaFreeHost(mem); break;
+      case DataLocation::CPU_PINNED:
+        if (!alloc_bytes || !detail::PinnedPool::instance().put(mem, alloc_bytes)) cudaFreeHost(mem);
+        break;
       case DataLocation::CPU_MALLOC: std::free(mem); break;
       default: break;  // FOREIGN_*: never freed (src/ggnn/base/data.cu:147-149)
     }
