@@ -630,6 +630,41 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s):
                           "tensor_pipe": load_profile_note("bf_tc")}
     except Exception as e:  # noqa: BLE001
         ex["bf_query"] = {"error": repr(e)[-300:]}
+    # native uint8 rows: bench.py's vectors are integer-valued in [0, 255], so the SAME base, queries and
+    # graph can be searched from 1-byte rows -- results must be identical, the gather traffic is a quarter
+    try:
+        if bool((base == base.round()).all()) and float(base.min()) >= 0 and float(base.max()) <= 255:
+            g8 = ggnn.GGNN()
+            g8.set_return_results_on_gpu(True)
+            g8.set_base(base.to(torch.uint8))
+            g8._prepare(a.k_build)
+            g8._shards[0].graph = idx.get_graph(0)
+            g8._measure = 0
+            q8 = query.to(torch.uint8)
+            (i8, d8), ms8 = timed(lambda: g8.query(q8, K, a.tau_query, a.max_iterations), reps=10)
+            (i32, d32), ms32 = timed(lambda: idx.query(query, K, a.tau_query, a.max_iterations), reps=10)
+            st2 = [torch.cuda.Stream(dev) for _ in range(2)]
+
+            def piped(g, q, n=20):
+                for i in range(n):
+                    with torch.cuda.stream(st2[i % 2]):
+                        g.query(q, K, a.tau_query, a.max_iterations)
+                for s_ in st2:
+                    torch.cuda.current_stream(dev).wait_stream(s_)
+            _, p8 = timed(lambda: piped(g8, q8), reps=2)
+            _, p32 = timed(lambda: piped(idx, query), reps=2)
+            n_iter, n_dist, alg32 = _query_stats(idx, query, K, a.tau_query, a.max_iterations)
+            cfg = idx.get_graph(0).config
+            alg8 = 1.0 * cfg.D * (Nq + n_dist) + 4.0 * cfg.KBuild * n_iter + (4.0 * cfg.S + 8.0 * K) * Nq
+            ex["uint8_native"] = {"what": "same base / queries / graph as the headline, vectors stored as uint8 (1-byte rows, integer dp4a distances)",
+                                  "single_batch_ms": ms8, "fp32_single_batch_ms": ms32, "pipelined_ms_per_batch": p8 / 20,
+                                  "fp32_pipelined_ms_per_batch": p32 / 20, "queries_per_s_pipelined": Nq / (p8 / 20 * 1e-3),
+                                  "results_identical_to_fp32": bool(torch.equal(i8, i32) and torch.equal(d8, d32)),
+                                  "algorithmic_bytes_per_launch": alg8, "fp32_algorithmic_bytes_per_launch": alg32,
+                                  "base_bytes": int(base.numel()), "fp32_base_bytes": int(base.numel() * 4)}
+            del g8
+    except Exception as e:  # noqa: BLE001
+        ex["uint8_native"] = {"error": repr(e)[-300:]}
     # a harder data set (intrinsic dimension 16): operating point found by sweeping the REFERENCE first
     # (profiles/r02_reference_sweep_manifold16.json, procedure of ggnn_benchmark.cpp:186-200)
     try:
@@ -885,7 +920,7 @@ def main():
     ap.add_argument("--c3-n", dest="c3_n", type=int, default=10_000_000)
     ap.add_argument("--hard-kind", dest="hard_kind", default="manifold16")
     ap.add_argument("--hard-tau", dest="hard_tau", type=float, default=1.0)
-    ap.add_argument("--hard-iterations", dest="hard_iterations", type=int, default=400)
+    ap.add_argument("--hard-iterations", dest="hard_iterations", type=int, default=200)
     for k, v in DEF.items():
         ap.add_argument("--" + k.replace("_", "-"), type=type(v), default=v)
     a = ap.parse_args()

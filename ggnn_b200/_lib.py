@@ -42,6 +42,7 @@ class QueryParams(C.Structure):
         ("n_scatter", C.c_uint32), ("scatter_slot", C.c_uint32), ("scatter_rows", C.c_uint32),
         ("scatter_dists_offset", C.c_size_t), ("d_scatter_dst", C.c_void_p), ("d_scatter_flags", C.c_void_p),
         ("d_scatter_done", C.c_void_p),
+        ("base_type", C.c_uint32),   # 0 fp32, 1 native uint8 rows (d_base / d_query are uint8 then)
     ]
 
 
@@ -60,7 +61,7 @@ EXPORTS = [
     "ggnn_b200_merge", "ggnn_b200_sym", "ggnn_b200_sym_buffer_merge", "ggnn_b200_build_graph",
     "ggnn_b200_merge_topk", "ggnn_b200_widen_u8",
     "ggnn_b200_ipc_alloc", "ggnn_b200_ipc_open", "ggnn_b200_ipc_close", "ggnn_b200_ipc_free", "ggnn_b200_peer_enable",
-    "ggnn_b200_wait_flag",
+    "ggnn_b200_wait_flag", "ggnn_b200_refine_graph", "ggnn_b200_rng_create", "ggnn_b200_rng_fill_build", "ggnn_b200_rng_destroy",
 ]
 
 _lib = None
@@ -108,6 +109,11 @@ def lib():
         l.ggnn_b200_ipc_free.argtypes = [vp]
         l.ggnn_b200_peer_enable.argtypes = [C.c_int]
         l.ggnn_b200_wait_flag.argtypes = [vp, u32, u32, vp, vp]
+        l.ggnn_b200_refine_graph.argtypes = [cfgp, vp, i32, f32, vp, vp, sz, vp]
+        l.ggnn_b200_rng_create.argtypes = [C.POINTER(vp), C.c_uint64]
+        l.ggnn_b200_rng_fill_build.argtypes = [vp, cfgp, vp, vp]
+        l.ggnn_b200_rng_destroy.argtypes = [vp]
+        l.ggnn_b200_rng_destroy.restype = None
         _lib = l
     return _lib
 

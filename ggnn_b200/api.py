@@ -87,7 +87,9 @@ class Graph:
 class _Shard:
     def __init__(self, device, base, global_id, pool=None, host_rows=None):
         self.device = device
-        self.base = base          # [N_shard, D] fp32 on `device` (None in swap mode: see ggnn_b200/swap.py)
+        self.base = base          # [N_shard, D] fp32 on `device` (None in swap mode: see ggnn_b200/swap.py; None for a
+                                  # uint8 base until a kernel needs widened rows: GGNN._f32)
+        self.base_u8 = None       # [N_shard, D] uint8 on `device`: native rows of a uint8 base (resident mode)
         self.global_id = global_id
         self.graph = None         # Graph (resident mode)
         self.pool = pool          # swap.ShardPool of this shard's GPU, or None = everything stays resident
@@ -162,16 +164,17 @@ class GGNN:
         base = _as_tensor(base, "base")
         if base.dtype not in (torch.float32, torch.uint8):
             raise TypeError("base must be float32 or uint8 (lib.h:26-28)")
-        # uint8 base vectors (the reference's BaseT = uint8_t instantiation, lib.h:26-28): every distance of the
-        # reference is computed on static_cast<float>(value) (distance.cuh:131-148), so widening the vectors to
-        # fp32 once gives bit-identical results with the fp32 kernels.  (A native 1-byte row format -- 4x less gather
-        # traffic -- is the next step)
+        # uint8 base vectors (the reference's BaseT = uint8_t instantiation, lib.h:26-28) stay uint8: the traversal
+        # kernel reads the 1-byte rows natively (a quarter of the gather traffic and of the memory; integer dp4a
+        # arithmetic, exact for D <= 256).  Every distance of the reference is computed on static_cast<float>(value)
+        # (distance.cuh:131-148), so the kernels without a native variant (construction, brute force, other query shapes)
+        # run on rows widened to fp32 on the device for the duration of the call: bit-identical results.
         self._base_dtype = base.dtype
         if self._shards:
             raise RuntimeError("base cannot be changed after the graph has been set up")
         if not (self.MIN_D <= base.shape[1] <= self.MAX_D):
             raise ValueError("unsupported dimension")
-        self._base = base.contiguous().float() if base.dtype == torch.uint8 else base.contiguous()  # (the reference copies too)
+        self._base = base.contiguous()  # (used in place; the reference copies)
 
     # ---- sharding (ggnn.cu:154-203) ----
     def _prepare(self, k_build):
@@ -217,10 +220,29 @@ class GGNN:
             for s in range(self._spg):
                 gid = gi * self._spg + s
                 rows = self._base[gid * n_shard:(gid + 1) * n_shard]
-                if pool is None:
+                if pool is None and rows.dtype == torch.uint8:
+                    sh = _Shard(dev, None, gid)
+                    sh.base_u8 = rows.to(dev, non_blocking=True).contiguous()
+                    self._shards.append(sh)
+                elif pool is None:
                     self._shards.append(_Shard(dev, rows.to(dev, non_blocking=True).contiguous(), gid))
                 else:
                     self._shards.append(_Shard(dev, None, gid, pool, rows))
+
+    def _f32(self, sh):
+        """fp32 rows of a resident shard; the rows of a uint8 base are widened on the device on demand (exact)"""
+        if sh.base is None and sh.base_u8 is not None:
+            with torch.cuda.device(sh.device):
+                out = torch.empty(sh.base_u8.shape, dtype=torch.float32, device=sh.device)
+                _lib.check(_lib.lib().ggnn_b200_widen_u8(_ptr(sh.base_u8), _ptr(out), sh.base_u8.numel(), _stream_ptr(sh.device)))
+            sh.base = out
+        return sh.base
+
+    @staticmethod
+    def _drop_f32(sh):
+        """release the widened copy of a uint8 shard again (GGNN_B200_KEEP_WIDENED=1 keeps it)"""
+        if sh.base_u8 is not None and not os.environ.get("GGNN_B200_KEEP_WIDENED"):
+            sh.base = None
 
     def _cfg(self):
         return _lib.graph_config(self._n_shard, self._base.shape[1], self._kbuild)
@@ -235,7 +257,7 @@ class GGNN:
         for i, sh in enumerate(self._shards):
             with torch.cuda.device(sh.device):
                 if sh.pool is None:
-                    base, blob = sh.base, torch.zeros(blob_bytes, dtype=torch.uint8, device=sh.device)
+                    base, blob = self._f32(sh), torch.zeros(blob_bytes, dtype=torch.uint8, device=sh.device)
                 else:  # swap mode: build in a pool slot, start loading the next shard of this GPU meanwhile
                     base, blob = sh.pool.acquire(sh.global_id, sh.host_rows)
                     blob.zero_()
@@ -243,16 +265,37 @@ class GGNN:
                     if nxt is not None and nxt.pool is sh.pool:
                         sh.pool.prefetch(nxt.global_id, nxt.host_rows, keep=(sh.global_id,))
                 scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=sh.device)
+                # one cuRAND generator (XORWOW, seed 1234) per GPU whose sequence continues over the shards built on it,
+                # like the reference's (graph_construction.cu:96-102,127): every shard gets the reference's selection
+                rng = self._rng(sh.device)
+                d_rng = torch.empty(cfg.Ns[0] + cfg.Ns[1] + cfg.Ns[2], dtype=torch.float32, device=sh.device)
+                _lib.check(l.ggnn_b200_rng_fill_build(rng, C.byref(cfg), _ptr(d_rng), _stream_ptr(sh.device)))
                 _lib.check(l.ggnn_b200_build_graph(C.byref(cfg), _ptr(base), int(measure), float(tau_build),
-                                                   int(refinement_iterations), None, _ptr(blob), _ptr(scratch),
+                                                   int(refinement_iterations), _ptr(d_rng), _ptr(blob), _ptr(scratch),
                                                    scratch_bytes, _stream_ptr(sh.device)))
                 if sh.pool is None:
                     sh.graph = Graph(cfg, blob)
                 else:
                     sh.pool.mark_built(sh.global_id)
                 torch.cuda.current_stream(sh.device).synchronize()
-                del scratch
+                del scratch, base
+                self._drop_f32(sh)
         self._measure = int(measure)
+
+    def _rng(self, device):
+        rngs = self.__dict__.setdefault("_rngs", {})
+        if device not in rngs:
+            h = C.c_void_p()
+            _lib.check(_lib.lib().ggnn_b200_rng_create(C.byref(h), 1234))
+            rngs[device] = h
+        return rngs[device]
+
+    def __del__(self):
+        try:
+            for h in self.__dict__.get("_rngs", {}).values():
+                _lib.lib().ggnn_b200_rng_destroy(h)
+        except Exception:  # interpreter shutdown
+            pass
 
     def _has_graph(self):
         return bool(self._shards) and all((sh.graph is not None) if sh.pool is None else (sh.global_id in sh.pool.has_graph)
@@ -318,6 +361,7 @@ class GGNN:
             if scatter is None:
                 ids = torch.empty((Nq, k_query * self._spg), dtype=torch.int32, device=dev)
                 dists = torch.empty((Nq, k_query * self._spg), dtype=torch.float32, device=dev)
+            q_f32 = None
             order = list(range(len(shards)))
             pool = shards[0].pool
             if pool is not None:
@@ -337,7 +381,20 @@ class GGNN:
                 p.D, p.measure, p.KQuery = cfg.D, int(measure), int(k_query)
                 p.tau_query, p.max_iterations = float(tau_query), int(max_iterations)
                 p.N_base, p.KBuild, p.num_starting_points = cfg.N, cfg.KBuild, cfg.S
-                p.d_base, p.d_query = sh_base.data_ptr(), q_dev.data_ptr()
+                # uint8 base: native 1-byte rows where the kernel has a variant, else rows widened on the device
+                native = (sh.pool is None and sh.base_u8 is not None and q_dev.dtype == torch.uint8 and
+                          cfg.D % 16 == 0 and cfg.D <= 256 and int(k_query) <= 47 and
+                          not os.environ.get("GGNN_B200_NO_NATIVE_U8"))
+                if native:
+                    p.base_type = 1
+                    p.d_base, p.d_query = sh.base_u8.data_ptr(), q_dev.data_ptr()
+                else:
+                    if sh_base is None:
+                        sh_base = self._f32(sh)
+                    if q_dev.dtype == torch.uint8:
+                        if q_f32 is None:
+                            q_f32 = q_dev.float()
+                    p.d_base, p.d_query = sh_base.data_ptr(), (q_f32 if q_f32 is not None else q_dev).data_ptr()
                 p.d_graph = sh_graph.graph.data_ptr()
                 p.d_starting_points = sh_graph.layer_translation(_lib.L - 1).data_ptr()
                 p.d_nn1_stats = sh_graph.nn1_stats.data_ptr()
@@ -364,8 +421,6 @@ class GGNN:
         query = _as_tensor(query, "query")
         if query.dtype != getattr(self, "_base_dtype", torch.float32):
             raise ValueError("query data type has to match base data type")  # ggnn.cu:524-540
-        if query.dtype == torch.uint8:
-            query = query.float()
         if query.shape[1] != self._base.shape[1]:
             raise ValueError("query dimension does not match the base")
         l = _lib.lib()
@@ -466,8 +521,6 @@ class GGNN:
                 st.wait_event(start)
                 with torch.cuda.stream(st):
                     q_dev = query[lo:hi].to(dev, non_blocking=True)
-                    if q_dev.dtype == torch.uint8:
-                        q_dev = q_dev.float()
                     ids, dists = self._query_device(0, q_dev.contiguous(), k_query, tau_query, max_iterations, measure)
                     out_i[lo:hi].copy_(ids, non_blocking=True)
                     out_d[lo:hi].copy_(dists, non_blocking=True)
@@ -484,15 +537,18 @@ class GGNN:
         query = _as_tensor(query, "query")
         if query.dtype != getattr(self, "_base_dtype", torch.float32):
             raise ValueError("query data type has to match base data type")
-        if query.dtype == torch.uint8:
-            query = query.float()
         dev = torch.device("cuda", self._gpus[0])
         with torch.cuda.device(dev):
-            if self._shards and len(self._shards) == 1 and self._shards[0].pool is None:
-                base = self._shards[0].base
+            single = self._shards[0] if (self._shards and len(self._shards) == 1 and self._shards[0].pool is None) else None
+            if single is not None:
+                base = self._f32(single)
             else:
-                base = self._base.to(dev).contiguous()
-            ids, dists = self._bf_query_rows(base, query.to(dev).contiguous(), int(k_gt), int(measure))
+                base = self._base.to(dev).contiguous().float()
+            ids, dists = self._bf_query_rows(base, query.to(dev).contiguous().float(), int(k_gt), int(measure))
+            del base
+            if single is not None:
+                torch.cuda.current_stream(dev).synchronize()
+                self._drop_f32(single)
         if self._results_on_gpu:
             return ids, dists
         return ids.cpu(), dists.cpu()

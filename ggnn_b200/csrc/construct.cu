@@ -1347,16 +1347,69 @@ extern "C" int ggnn_b200_build_graph(const ggnn_b200_graph_config* cfg, const fl
     }
   }
   // refine: :141-147
-  for (uint32_t it = 0; it < refinement_iterations && !rc; ++it) {
-    for (uint32_t layer = L - 2; layer != 0xffffffffu && !rc; --layer) {
-      merge_step(L - 1, layer);
-      if (rc) break;
-      sym_pass(layer);
-    }
-  }
+  for (uint32_t it = 0; it < refinement_iterations && !rc; ++it)
+    rc = ggnn_b200_refine_graph(cfg, d_base, measure, tau_build, d_graph_blob, d_scratch, scratch_bytes, stream_);
   if (gen) {
     cudaStreamSynchronize(stream);  // the generator must outlive its queued work
     curandDestroyGenerator(gen);
   }
   return rc;
+}
+
+extern "C" int ggnn_b200_refine_graph(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, float tau_build,
+                                      void* d_graph_blob, void* d_scratch, size_t scratch_bytes, ggnn_b200_stream_t stream)
+{
+  if (int rc = check_cfg(cfg)) return rc;
+  if (!d_base || !d_graph_blob || !d_scratch) return set_error(GGNN_B200_ERR_INVALID, "null pointer");
+  if (scratch_bytes < ggnn_b200_build_scratch_bytes(cfg)) return set_error(GGNN_B200_ERR_INVALID, "scratch too small");
+  const Scratch s = scratch_layout(*cfg, d_scratch);
+  const GraphPtrs g = graph_ptrs(*cfg, d_graph_blob);
+  constexpr uint32_t L = GGNN_B200_L;
+  for (uint32_t layer = L - 2; layer != 0xffffffffu; --layer) {
+    if (int rc = ggnn_b200_merge(cfg, d_base, measure, tau_build, L - 1, layer, d_graph_blob, s.graph_buffer, s.nn1, stream)) return rc;
+    if (!layer)
+      if (int rc = ggnn_b200_nn1_stats(s.nn1, cfg->N, g.nn1_stats, s.stats, stream)) return rc;
+    if (int rc = ggnn_b200_sym(cfg, d_base, measure, tau_build, layer, d_graph_blob, s.sym_buffer, s.sym_atomic, stream)) return rc;
+    if (int rc = ggnn_b200_sym_buffer_merge(cfg, layer, s.sym_buffer, s.sym_atomic, d_graph_blob, stream)) return rc;
+  }
+  return 0;
+}
+
+struct ggnn_b200_rng {
+  curandGenerator_t gen;
+};
+
+extern "C" int ggnn_b200_rng_create(ggnn_b200_rng** out, uint64_t seed)
+{
+  if (!out) return set_error(GGNN_B200_ERR_INVALID, "null pointer");
+  curandGenerator_t gen = nullptr;
+  if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS ||
+      curandSetPseudoRandomGeneratorSeed(gen, seed) != CURAND_STATUS_SUCCESS) {
+    if (gen) curandDestroyGenerator(gen);
+    return set_error(GGNN_B200_ERR_INVALID, "cuRAND generator setup failed");
+  }
+  *out = new ggnn_b200_rng{gen};
+  return 0;
+}
+
+extern "C" int ggnn_b200_rng_fill_build(ggnn_b200_rng* rng, const ggnn_b200_graph_config* cfg, float* d_rng, ggnn_b200_stream_t stream)
+{
+  if (!rng || !cfg || !d_rng) return set_error(GGNN_B200_ERR_INVALID, "null pointer");
+  if (curandSetStream(rng->gen, static_cast<cudaStream_t>(stream)) != CURAND_STATUS_SUCCESS)
+    return set_error(GGNN_B200_ERR_INVALID, "curandSetStream failed");
+  size_t off = 0;
+  for (uint32_t layer = 0; layer + 1 < GGNN_B200_L; ++layer) {  // one call per select(), like the reference
+    if (curandGenerateUniform(rng->gen, d_rng + off, cfg->Ns[layer]) != CURAND_STATUS_SUCCESS)
+      return set_error(GGNN_B200_ERR_INVALID, "curandGenerateUniform failed");
+    off += cfg->Ns[layer];
+  }
+  return 0;
+}
+
+extern "C" void ggnn_b200_rng_destroy(ggnn_b200_rng* rng)
+{
+  if (!rng) return;
+  cudaDeviceSynchronize();  // the generator must outlive its queued work
+  curandDestroyGenerator(rng->gen);
+  delete rng;
 }

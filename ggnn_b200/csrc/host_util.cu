@@ -53,7 +53,16 @@ const DeviceInfo& device_info()
   return infos[dev];
 }
 
+static int make_row_gather_tensor_map_any(TensorMapStorage* out, const void* d_base, uint64_t rows, uint32_t cols, bool u8);
 int make_row_gather_tensor_map(TensorMapStorage* out, const float* d_base, uint64_t rows, uint32_t cols)
+{
+  return make_row_gather_tensor_map_any(out, d_base, rows, cols, false);
+}
+int make_row_gather_tensor_map_u8(TensorMapStorage* out, const uint8_t* d_base, uint64_t rows, uint32_t cols)
+{
+  return make_row_gather_tensor_map_any(out, d_base, rows, cols, true);
+}
+static int make_row_gather_tensor_map_any(TensorMapStorage* out, const void* d_base, uint64_t rows, uint32_t cols, bool u8)
 {
   static_assert(sizeof(CUtensorMap) == sizeof(TensorMapStorage), "CUtensorMap is 128 bytes");
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -69,12 +78,13 @@ int make_row_gather_tensor_map(TensorMapStorage* out, const float* d_base, uint6
       encode = reinterpret_cast<EncodeFn>(fn);
   });
   if (!encode) return set_error(GGNN_B200_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-  if (cols == 0 || cols > 256 || cols % 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "row gather tensor map needs D % 4 == 0 and D <= 256");
+  if (!u8 && (cols == 0 || cols > 256 || cols % 4)) return set_error(GGNN_B200_ERR_UNSUPPORTED, "row gather tensor map needs D % 4 == 0 and D <= 256");
+  if (u8 && (cols == 0 || cols > 256 || cols % 16)) return set_error(GGNN_B200_ERR_UNSUPPORTED, "uint8 row gather tensor map needs D % 16 == 0 and D <= 256");
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * sizeof(float)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * (u8 ? 1 : sizeof(float))};
   const cuuint32_t box[2] = {cols, 1};
   const cuuint32_t elem_strides[2] = {1, 1};
-  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_base), dims,
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(d_base), dims,
                             strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -25,6 +25,8 @@ struct alignas(64) TensorMapStorage {
   unsigned char bytes[128];
 };
 int make_row_gather_tensor_map(TensorMapStorage* out, const float* d_base, uint64_t rows, uint32_t cols);
+// the same for uint8 rows of `cols` bytes (cols % 16 == 0, cols <= 256)
+int make_row_gather_tensor_map_u8(TensorMapStorage* out, const uint8_t* d_base, uint64_t rows, uint32_t cols);
 
 inline uint32_t bit_ceil_u32(uint32_t v)
 {

@@ -34,6 +34,47 @@ struct QueryArgs {
   TensorMapStorage tmap;  // gather4 staging (stage_mode 3): tensor map of the base
 };
 
+// query_layer.cu:81-90 (+ simple_knn_cache.cuh:344-352): the K best of query n into the (interleaved) result buffer and /
+// or, for the fused shard-merge exchange, straight into every destination GPU's gathered buffer (peer-mapped memory: the
+// stores travel over NVLink while the other warps keep traversing)
+template <class LT>
+__device__ __forceinline__ void write_query_results(const LT& L, const ggnn_b200_query_params& p, uint32_t n)
+{
+  if (p.d_query_results) {
+    const size_t row = (static_cast<size_t>(n) * p.shards_per_gpu + p.on_gpu_shard_id) * p.KQuery;
+    const int id_off = static_cast<int>(p.on_gpu_shard_id) * p.N_base;
+    L.write_results(p.d_query_results + row, p.d_query_results_dists ? p.d_query_results_dists + row : nullptr, p.KQuery,
+                    id_off);
+  }
+  if (p.n_scatter) {
+    const size_t srow = (static_cast<size_t>(p.scatter_slot) * p.scatter_rows + n) * p.KQuery;
+    for (uint32_t t = 0; t < p.n_scatter; ++t) {
+      char* dst = static_cast<char*>(p.d_scatter_dst[t]);
+      L.write_results(reinterpret_cast<int*>(dst) + srow, reinterpret_cast<float*>(dst + p.scatter_dists_offset) + srow,
+                      p.KQuery, 0);
+    }
+  }
+}
+
+// exchange: the last warp of the launch to get here bumps the flag word of every destination; every warp's result
+// stores are ordered before its count (system-scope fence), the count before the flags
+__device__ __forceinline__ void signal_exchange(const ggnn_b200_query_params& p, uint32_t total_warps)
+{
+  if (p.n_scatter && p.d_scatter_done) {
+    const int lane = lane_id();
+    __threadfence_system();
+    unsigned old = 0;
+    if (lane == 0) old = atomicAdd(p.d_scatter_done, 1u);
+    old = __shfl_sync(FULL, old, 0);
+    if (old == total_warps - 1) {
+      if (lane == 0) *p.d_scatter_done = 0;  // ready for the next launch on this stream
+      __threadfence_system();
+      if (p.d_scatter_flags)
+        for (uint32_t t = lane; t < p.n_scatter; t += 32) atomicAdd_system(p.d_scatter_flags[t], 1u);
+    }
+  }
+}
+
 // LT = WarpLists<NS> (best list + prioQ in registers, sorted_size <= 256) or SmemLists (anything larger)
 template <class LT, bool FAST, int NI, bool G4 = false>
 __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) query_kernel(const __grid_constant__ QueryArgs a)
@@ -119,23 +160,7 @@ __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) qu
       }
     }
 
-    // :81-90 (+ simple_knn_cache.cuh:344-352)
-    if (p.d_query_results) {
-      const size_t row = (static_cast<size_t>(n) * p.shards_per_gpu + p.on_gpu_shard_id) * p.KQuery;
-      const int id_off = static_cast<int>(p.on_gpu_shard_id) * p.N_base;
-      L.write_results(p.d_query_results + row, p.d_query_results_dists ? p.d_query_results_dists + row : nullptr, p.KQuery,
-                      id_off);
-    }
-    // fused shard-merge exchange: this query's list goes straight into every destination GPU's gathered buffer
-    // (peer-mapped memory: the stores travel over NVLink while the other warps keep traversing)
-    if (p.n_scatter) {
-      const size_t srow = (static_cast<size_t>(p.scatter_slot) * p.scatter_rows + n) * p.KQuery;
-      for (uint32_t t = 0; t < p.n_scatter; ++t) {
-        char* dst = static_cast<char*>(p.d_scatter_dst[t]);
-        L.write_results(reinterpret_cast<int*>(dst) + srow, reinterpret_cast<float*>(dst + p.scatter_dists_offset) + srow,
-                        p.KQuery, 0);
-      }
-    }
+    write_query_results(L, p, n);
     if (p.d_stats && lane == 0) {
       p.d_stats[2 * static_cast<size_t>(n)] = st.pops;
       p.d_stats[2 * static_cast<size_t>(n) + 1] = st.dists;
@@ -150,20 +175,7 @@ __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) qu
     }
   }
 
-  // exchange: the last warp of the launch to get here bumps the flag word of every destination; every warp's result
-  // stores are ordered before its count (system-scope fence), the count before the flags
-  if (p.n_scatter && p.d_scatter_done) {
-    __threadfence_system();
-    unsigned old = 0;
-    if (lane == 0) old = atomicAdd(p.d_scatter_done, 1u);
-    old = __shfl_sync(FULL, old, 0);
-    if (old == total_warps - 1) {
-      if (lane == 0) *p.d_scatter_done = 0;  // ready for the next launch on this stream
-      __threadfence_system();
-      if (p.d_scatter_flags)
-        for (uint32_t t = lane; t < p.n_scatter; t += 32) atomicAdd_system(p.d_scatter_flags[t], 1u);
-    }
-  }
+  signal_exchange(p, total_warps);
 }
 
 template <class LT, bool FAST, int NI, bool G4 = false>
@@ -174,6 +186,190 @@ static int launch(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(query_kernel)");
   kern<<<grid, a.warps_per_cta * 32, smem, stream>>>(a);
   return set_cuda_error(cudaGetLastError(), "query_kernel launch");
+}
+
+
+// ================================================================================================
+// native uint8 rows (BaseT = uint8_t, include/ggnn/base/lib.h:26-28): rows of D bytes staged by TMA gather4 (32 rows of
+// 128 bytes fit where 8 fp32 rows did), distances in integer arithmetic -- per row and lane one LDS.32 (4 dims), one
+// VABSDIFF4, one IDP4A, and ONE warp-wide integer REDUX instead of a shuffle tree.  Exact: every partial sum is an integer
+// below 2^24 for D <= 256, so the reference's fp32 accumulation of static_cast<float>(value) terms
+// (distance.cuh:104-148) yields the same numbers in any order.
+// ================================================================================================
+template <class LT, int W, bool FULLW, bool FILTER>
+__device__ __forceinline__ void fetch_u8(LT& L, const VisitedSet& V, WarpSmem& ws, const uint32_t (&q)[W], float q_norm, int measure,
+                                         uint32_t words, int ck, float xi, Stats& st, const int* __restrict__ pf_graph,
+                                         uint32_t pf_stride, SpecRow* spec)
+{
+  const int lane = lane_id();
+  bool valid = ck != EMPTY_KEY;
+  if constexpr (FILTER) {
+    __syncwarp();
+    L.store_keys(ws.s_sorted);
+    __syncwarp();
+    if (valid) valid = !L.in_sorted(ws.s_sorted, ck) && !V.contains(ck);
+  }
+  const unsigned mask = __ballot_sync(FULL, valid);
+  const int cnt = __popc(mask);
+  if (cnt == 0) return;
+  st.dists += cnt;
+  __syncwarp();
+  if (valid) ws.s_sorted[__popc(mask & ((1u << lane) - 1u))] = ck;
+  __syncwarp();
+  const int key_r = ws.s_sorted[lane];
+
+  // all rows of the fetch in flight at once: lane 4j fetches candidates 4j .. 4j+3 with ONE instruction
+  const uint32_t row_bytes = words * 4u;
+  const int mp = lane < cnt ? key_r : ws.pad_row;
+  const int m1 = __shfl_down_sync(FULL, mp, 1);
+  const int m2 = __shfl_down_sync(FULL, mp, 2);
+  const int m3 = __shfl_down_sync(FULL, mp, 3);
+  const uint32_t bar_s = smem_u32(ws.bar);
+  if (lane == 0) mbar_expect_tx_s(bar_s, static_cast<uint32_t>((cnt + 3) & ~3) * row_bytes);
+  if ((lane & 3) == 0 && lane < cnt)
+    tma_gather4_s(smem_u32(ws.stage) + static_cast<uint32_t>(lane) * row_bytes, ws.tmap, mp, m1, m2, m3, bar_s);
+  mbar_wait_s(bar_s, ws.parity & 1u);
+  ws.parity ^= 1u;
+
+  const uint32_t* rows = reinterpret_cast<const uint32_t*>(ws.stage);
+  float mine = G200_INF;
+  for (int r0 = 0; r0 < cnt; r0 += 4) {  // (rows past cnt hold zero fill or stale bytes: their results are never used)
+    unsigned acc[4], nrm[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[i] = 0u;
+      nrm[i] = 0u;
+      const uint32_t* row = rows + static_cast<uint32_t>(r0 + i) * words;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t idx = lane + 32u * w;
+        const uint32_t b = (FULLW || idx < words) ? row[idx] : 0u;
+        if (measure == 0) {
+          const uint32_t s = __vabsdiffu4(b, q[w]);
+          acc[i] = __dp4a(s, s, acc[i]);
+        }
+        else {
+          acc[i] = __dp4a(b, q[w], acc[i]);
+          nrm[i] = __dp4a(b, b, nrm[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned tot = __reduce_add_sync(FULL, acc[i]);
+      float d = static_cast<float>(tot);
+      if (measure != 0) d = cosine_finish(d, static_cast<float>(__reduce_add_sync(FULL, nrm[i])), q_norm);
+      if (lane == r0 + i) mine = d;
+    }
+  }
+  __syncwarp();  // all reads of the stage are done before the next fetch overwrites it
+  finish_fetch<LT, FILTER>(L, key_r, mine, cnt, xi, pf_graph, pf_stride, spec);
+}
+
+template <class LT, int W, bool FULLW>
+__global__ void __launch_bounds__(128, 6) query_kernel_u8(const __grid_constant__ QueryArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const ggnn_b200_query_params& p = a.p;
+  unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * a.warp_smem_bytes;
+  WarpSmem ws;
+  ws.stage = reinterpret_cast<float*>(wbase);
+  ws.s_q = nullptr;
+  ws.s_sorted = reinterpret_cast<int*>(wbase + a.off_sorted);
+  ws.bar = reinterpret_cast<uint64_t*>(wbase + a.off_bar);
+  ws.parity = 0;
+  ws.stage_rows = 32;
+  ws.stage_mode = 3;
+  ws.tmap = &a.tmap;
+  ws.pad_row = a.pad_row;
+  if (lane == 0) mbar_init(&ws.bar[0], 1);
+  mbar_fence_init();
+  __syncwarp();
+
+  VisitedSet V;
+  V.tab = reinterpret_cast<int*>(wbase + a.off_hash);
+  V.hmask = a.hsize - 1;
+  V.hshift = 32 - (31 - __clz(a.hsize));
+  V.ring = a.ring_cap ? reinterpret_cast<int*>(wbase + a.off_ring) : nullptr;
+  V.vcap = p.cache_size - p.sorted_size;
+  V.vpos = 0;
+
+  const uint32_t words = p.D / 4;
+  const uint8_t* base_q = reinterpret_cast<const uint8_t*>(p.d_query);
+  const float max_nn1 = p.d_nn1_stats[1];
+  const float xi = (p.measure == 0) ? __fmul_rn(__fmul_rn(__fmul_rn(max_nn1, max_nn1), p.tau_query), p.tau_query)
+                                    : __fmul_rn(max_nn1, p.tau_query);
+  const uint32_t total_warps = gridDim.x * a.warps_per_cta;
+  uint32_t n = blockIdx.x * a.warps_per_cta + warp;
+  if (p.d_work_counter) {
+    if (lane == 0) n = atomicAdd(p.d_work_counter, 1u);
+    n = __shfl_sync(FULL, n, 0);
+  }
+  const bool use_spec = a.prefetch >= 2 && p.KBuild <= 32;
+
+  while (n < a.N_query) {
+    uint32_t q[W];
+    const uint32_t* gq = reinterpret_cast<const uint32_t*>(base_q + static_cast<size_t>(n) * p.D);
+    unsigned qn = 0u;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const uint32_t idx = lane + 32u * w;
+      q[w] = (FULLW || idx < words) ? gq[idx] : 0u;
+      qn = __dp4a(q[w], q[w], qn);
+    }
+    const float q_norm = static_cast<float>(__reduce_add_sync(FULL, qn));  // distance.cuh:104-117 (exact)
+    LT L;
+    L.init(p.KQuery, nullptr, p.sorted_size);
+    V.clear();
+    Stats st{0, 0};
+
+    for (uint32_t i = 0; i < p.num_starting_points; i += 32) {  // query_layer.cu:55
+      const int ck = (i + lane < p.num_starting_points) ? p.d_starting_points[i + lane] : EMPTY_KEY;
+      fetch_u8<LT, W, FULLW, false>(L, V, ws, q, q_norm, p.measure, words, ck, xi, st, a.prefetch ? p.d_graph : nullptr, p.KBuild, nullptr);
+    }
+    SpecRow spec{EMPTY_KEY, EMPTY_KEY};
+    for (uint32_t ite = 0; ite < p.max_iterations; ++ite) {  // :58-76
+      const float best0 = L.dist_at(0);
+      const float r_xi = (p.measure == 0) ? fminf(xi, __fmul_rn(__fmul_rn(best0, p.tau_query), p.tau_query))
+                                          : fminf(xi, __fmul_rn(best0, p.tau_query));
+      const float crit = L.dist_at(L.BEST - 1) + r_xi;
+      const int anchor = L.pop(crit);
+      if (anchor == EMPTY_KEY) break;
+      V.insert(anchor);
+      st.pops++;
+      for (uint32_t i = 0; i < p.KBuild; i += 32) {
+        int ck;
+        if (use_spec && spec.key == anchor) ck = spec.row;
+        else ck = (i + lane < p.KBuild) ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane) : EMPTY_KEY;
+        spec.key = EMPTY_KEY;
+        fetch_u8<LT, W, FULLW, true>(L, V, ws, q, q_norm, p.measure, words, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr, p.KBuild,
+                                     use_spec ? &spec : nullptr);
+      }
+    }
+    write_query_results(L, p, n);
+    if (p.d_stats && lane == 0) {
+      p.d_stats[2 * static_cast<size_t>(n)] = st.pops;
+      p.d_stats[2 * static_cast<size_t>(n) + 1] = st.dists;
+    }
+    if (p.d_work_counter) {
+      if (lane == 0) n = atomicAdd(p.d_work_counter, 1u);
+      n = __shfl_sync(FULL, n, 0);
+    }
+    else n += total_warps;
+  }
+  signal_exchange(p, total_warps);
+}
+
+template <class LT, int W, bool FULLW>
+static int launch_u8(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream)
+{
+  auto kern = query_kernel_u8<LT, W, FULLW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(query_kernel_u8)");
+  kern<<<grid, a.warps_per_cta * 32, smem, stream>>>(a);
+  return set_cuda_error(cudaGetLastError(), "query_kernel_u8 launch");
 }
 
 }  // namespace g200
@@ -232,6 +428,57 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   if (p.d_work_counter) {
     cudaError_t e = cudaMemsetAsync(p.d_work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(work counter)");
+  }
+
+  if (p.base_type == GGNN_B200_BASE_U8) {
+    // native uint8 rows: register lists (sorted_size <= 64), D a multiple of 16 (TMA rows) and <= 256 (exactness bound)
+    if (smem_lists || NS > 2 || p.D % 16 || p.D > 256)
+      return set_error(GGNN_B200_ERR_UNSUPPORTED, "native uint8 query: needs D % 16 == 0, D <= 256 and KQuery <= 47 (widen to fp32 otherwise)");
+    if (make_row_gather_tensor_map_u8(&a.tmap, reinterpret_cast<const uint8_t*>(p.d_base), static_cast<uint64_t>(p.N_base), p.D))
+      return GGNN_B200_ERR_UNSUPPORTED;
+    const DeviceInfo& dev = device_info();
+    const uint32_t vcap = p.cache_size - p.sorted_size;
+    a.ring_cap = (vcap < p.max_iterations) ? vcap : 0;
+    a.hsize = std::max(64u, bit_ceil_u32(p.max_iterations + p.max_iterations / 4 + 1));
+    a.pad_row = p.N_base;  // out of bounds: zero fill, no memory traffic
+    a.stage_rows = 32;
+    a.stage_mode = 3;
+    a.prefetch = env_u32("GGNN_B200_QUERY_PREFETCH", 2);
+    a.warps_per_cta = 4;
+    uint32_t off = align_up(32u * p.D, 128);
+    a.off_sq = off;
+    a.off_sorted = off;
+    off += p.sorted_size * 4;
+    a.off_lists = off;
+    a.off_hash = off;
+    off += a.hsize * 4;
+    a.off_ring = off;
+    off += align_up(a.ring_cap * 4, 16);
+    a.off_bar = off;
+    off += 32;
+    a.warp_smem_bytes = align_up(off, 128);
+    const size_t smem = static_cast<size_t>(a.warp_smem_bytes) * a.warps_per_cta;
+    if (smem > dev.smem_per_block_optin) return set_error(GGNN_B200_ERR_UNSUPPORTED, "per-CTA shared memory exceeds the device limit");
+    a.N_query = N_query;
+    const uint32_t ctas_needed = (N_query + a.warps_per_cta - 1) / a.warps_per_cta;
+    uint32_t grid = ctas_needed;
+    if (p.d_work_counter) {
+      const uint32_t per_sm = std::max<uint32_t>(1, std::min<uint32_t>(6, dev.smem_per_sm / (smem + 1024)));
+      grid = std::min(ctas_needed, per_sm * dev.num_sms);
+    }
+    const bool fullw = (p.D % 128) == 0;
+    const int W = (p.D + 127) / 128;
+    switch (NS * 100 + W * 10 + (fullw ? 1 : 0)) {
+      case 111: return launch_u8<WarpLists<1>, 1, true>(a, grid, smem, stream);
+      case 110: return launch_u8<WarpLists<1>, 1, false>(a, grid, smem, stream);
+      case 121: return launch_u8<WarpLists<1>, 2, true>(a, grid, smem, stream);
+      case 120: return launch_u8<WarpLists<1>, 2, false>(a, grid, smem, stream);
+      case 211: return launch_u8<WarpLists<2>, 1, true>(a, grid, smem, stream);
+      case 210: return launch_u8<WarpLists<2>, 1, false>(a, grid, smem, stream);
+      case 221: return launch_u8<WarpLists<2>, 2, true>(a, grid, smem, stream);
+      case 220: return launch_u8<WarpLists<2>, 2, false>(a, grid, smem, stream);
+    }
+    return set_error(GGNN_B200_ERR_UNSUPPORTED, "no uint8 kernel variant");
   }
 
   // the FAST variants (query vector in registers) exist for NS <= 2; everything else takes the generic kernel

@@ -278,6 +278,64 @@ struct SpecRow {
   int row;  // lane l: adjacency entry l of `key`
 };
 
+// Second half of a fetch, shared by all row formats: lane r < cnt holds candidate key_r with distance `mine`
+// (adjacency order).  Speculative load of the next anchor's adjacency row, then the pushes in candidate order.
+template <class LT, bool FILTER>
+__device__ __forceinline__ void finish_fetch(LT& L, int key_r, float mine, int cnt, float xi, const int* __restrict__ pf_graph,
+                                             uint32_t pf_stride, SpecRow* spec)
+{
+  const int lane = lane_id();
+  // duplicates WITHIN this fetch (a graph row may name a point twice): only those can already be in the lists when
+  // their turn comes -- every other candidate passed the filter and nothing but its fellow candidates is pushed before it
+  unsigned dupmask = FULL;
+  if constexpr (FILTER) {
+    const unsigned same = __match_any_sync(FULL, lane < cnt ? key_r : (-2 - lane));
+    dupmask = __ballot_sync(FULL, (same & ((1u << lane) - 1u)) != 0u);
+  }
+  float best_last = L.dist_at(L.BEST - 1);  // criteria() = best_last + xi (simple_knn_cache.cuh:284)
+
+  if (pf_graph) {
+    const float crit0 = best_last + xi;
+    const bool pass = lane < cnt && mine < crit0;
+    if (spec && pf_stride <= 32) {
+      // predicted next anchor = min(current prioQ head, best passing candidate); distances are >= 0, so their bit
+      // patterns order like unsigned integers
+      const unsigned mbits = pass ? __float_as_uint(mine) : 0x7f800000u;
+      const unsigned best_bits = __reduce_min_sync(FULL, mbits);
+      const float head_d = L.dist_at(L.head);
+      int pred = L.key_at(L.head);
+      if (__uint_as_float(best_bits) < head_d) {
+        const unsigned who = __ballot_sync(FULL, pass && mbits == best_bits);
+        pred = __shfl_sync(FULL, key_r, __ffs(who) - 1);
+      }
+      spec->key = pred;
+      if (pred != EMPTY_KEY)
+        spec->row = (static_cast<uint32_t>(lane) < pf_stride) ? __ldg(pf_graph + static_cast<size_t>(pred) * pf_stride + lane)
+                                                            : EMPTY_KEY;
+    }
+    else if (pass) {
+      const int* row = pf_graph + static_cast<size_t>(key_r) * pf_stride;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + pf_stride - 1));
+    }
+  }
+
+  // pushes in candidate order; criteria() is re-read after each push (:284) -- it only changes when the push changed the
+  // last entry of the best list, i.e. when d < best_last (it never grows, so the pending mask only loses bits)
+  unsigned pm = __ballot_sync(FULL, mine < best_last + xi) & (cnt >= 32 ? FULL : ((1u << cnt) - 1u));
+  while (pm) {
+    const int c0 = __ffs(pm) - 1;
+    const int k = __shfl_sync(FULL, key_r, c0);
+    const float d = __shfl_sync(FULL, mine, c0);
+    L.push(k, d, (dupmask >> c0) & 1u);
+    pm &= pm - 1u;
+    if (d < best_last) {
+      best_last = L.dist_at(L.BEST - 1);
+      pm &= __ballot_sync(FULL, mine < best_last + xi);
+    }
+  }
+}
+
 template <class LT, bool FAST, int D32, int NW, bool FILTER, bool G4 = false>
 __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
                                       const QueryVec<FAST, D32, NW>& qv, const float* __restrict__ base,
@@ -378,55 +436,7 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
     }
   }
 
-  // duplicates WITHIN this fetch (a graph row may name a point twice): only those can already be in the lists when
-  // their turn comes -- every other candidate passed the filter and nothing but its fellow candidates is pushed before it
-  unsigned dupmask = FULL;
-  if constexpr (FILTER) {
-    const unsigned same = __match_any_sync(FULL, lane < cnt ? key_r : (-2 - lane));
-    dupmask = __ballot_sync(FULL, (same & ((1u << lane) - 1u)) != 0u);
-  }
-  float best_last = L.dist_at(L.BEST - 1);  // criteria() = best_last + xi (simple_knn_cache.cuh:284)
-
-  if (pf_graph) {
-    const float crit0 = best_last + xi;
-    const bool pass = lane < cnt && mine < crit0;
-    if (spec && pf_stride <= 32) {
-      // predicted next anchor = min(current prioQ head, best passing candidate); distances are >= 0, so their bit
-      // patterns order like unsigned integers
-      const unsigned mbits = pass ? __float_as_uint(mine) : 0x7f800000u;
-      const unsigned best_bits = __reduce_min_sync(FULL, mbits);
-      const float head_d = L.dist_at(L.head);
-      int pred = L.key_at(L.head);
-      if (__uint_as_float(best_bits) < head_d) {
-        const unsigned who = __ballot_sync(FULL, pass && mbits == best_bits);
-        pred = __shfl_sync(FULL, key_r, __ffs(who) - 1);
-      }
-      spec->key = pred;
-      if (pred != EMPTY_KEY)
-        spec->row = (static_cast<uint32_t>(lane) < pf_stride) ? __ldg(pf_graph + static_cast<size_t>(pred) * pf_stride + lane)
-                                                            : EMPTY_KEY;
-    }
-    else if (pass) {
-      const int* row = pf_graph + static_cast<size_t>(key_r) * pf_stride;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + pf_stride - 1));
-    }
-  }
-
-  // pushes in candidate order; criteria() is re-read after each push (:284) -- it only changes when the push changed the
-  // last entry of the best list, i.e. when d < best_last (it never grows, so the pending mask only loses bits)
-  unsigned pm = __ballot_sync(FULL, mine < best_last + xi) & (cnt >= 32 ? FULL : ((1u << cnt) - 1u));
-  while (pm) {
-    const int c0 = __ffs(pm) - 1;
-    const int k = __shfl_sync(FULL, key_r, c0);
-    const float d = __shfl_sync(FULL, mine, c0);
-    L.push(k, d, (dupmask >> c0) & 1u);
-    pm &= pm - 1u;
-    if (d < best_last) {
-      best_last = L.dist_at(L.BEST - 1);
-      pm &= __ballot_sync(FULL, mine < best_last + xi);
-    }
-  }
+  finish_fetch<LT, FILTER>(L, key_r, mine, cnt, xi, pf_graph, pf_stride, spec);
 }
 
 }  // namespace g200

@@ -675,18 +675,25 @@ class GGNN {
       const size_t scratch_bytes = ggnn_b200_build_scratch_bytes(&s.cfg);
       void* scratch = nullptr;
       detail::cuda_check(cudaMalloc(&scratch, scratch_bytes), "cudaMalloc(build scratch)");
+      float* d_rng = nullptr;
+      detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&d_rng), (static_cast<size_t>(s.cfg.Ns[0]) + s.cfg.Ns[1] + s.cfg.Ns[2]) * sizeof(float)),
+                         "cudaMalloc(build uniforms)");
       int rc = 0;
       for (uint32_t i = 0; i < s.spg && !rc; ++i) {
         Shard& sh = s.shards[g.first_shard + i];
         Slot& slot = acquire(g, sh);
         detail::cuda_check(cudaMemsetAsync(slot.blob.data(), 0, slot.blob.size_bytes(), g.stream), "cudaMemsetAsync");
+        // one cuRAND generator per GPU, continuing over its shards like the reference's (graph_construction.cu:96-102,127)
+        if (!g.rng) detail::abi_check(ggnn_b200_rng_create(&g.rng, 1234ULL));
+        detail::abi_check(ggnn_b200_rng_fill_build(g.rng, &s.cfg, d_rng, g.stream));
         rc = ggnn_b200_build_graph(&s.cfg, slot.base.data(), static_cast<int>(measure), tau_build, refinement_iterations,
-                                   nullptr, slot.blob.data(), scratch, scratch_bytes, g.stream);
+                                   d_rng, slot.blob.data(), scratch, scratch_bytes, g.stream);
         cudaStreamSynchronize(g.stream);
         sh.has_graph = rc == 0;
         sh.dirty = true;
       }
       cudaFree(scratch);
+      cudaFree(d_rng);
       detail::abi_check(rc);
     }
   }
@@ -1030,6 +1037,7 @@ class GGNN {
     cudaStream_t stream{nullptr};
     uint32_t* work_counter{nullptr};
     void** d_gather_tbl{nullptr};
+    ggnn_b200_rng* rng{nullptr};
     bool swap{false};
     uint32_t query_calls{0};
     uint64_t clock{0};
@@ -1066,6 +1074,7 @@ class GGNN {
         if (g.stream) cudaStreamDestroy(g.stream);
         if (g.work_counter) cudaFree(g.work_counter);
         if (g.d_gather_tbl) cudaFree(g.d_gather_tbl);
+        if (g.rng) ggnn_b200_rng_destroy(g.rng);
       }
     }
   };

@@ -111,7 +111,16 @@ typedef struct {
   void* const* d_scatter_dst;       /* device array [n_scatter] of destination buffer base pointers */
   uint32_t* const* d_scatter_flags; /* device array [n_scatter] of flag words (one per destination), or NULL */
   uint32_t* d_scatter_done;         /* local device word, zero before the first use (reset by every launch) */
+  /* --- native uint8 vectors (the reference's BaseT = uint8_t instantiation, include/ggnn/base/lib.h:26-28): with
+   * base_type = GGNN_B200_BASE_U8, d_base and d_query point to uint8 rows of D bytes (a quarter of the gather traffic).
+   * The reference computes every distance on static_cast<float>(value) (distance.cuh:104-148); for D <= 256 all
+   * partial sums are integers below 2^24, i.e. exact in fp32, so integer arithmetic (dp4a) gives bit-identical
+   * distances.  Shapes the native kernel does not cover return GGNN_B200_ERR_UNSUPPORTED (widen with
+   * ggnn_b200_widen_u8 and use the fp32 path: identical results). */
+  uint32_t base_type;
 } ggnn_b200_query_params;
+#define GGNN_B200_BASE_F32 0
+#define GGNN_B200_BASE_U8 1
 
 int ggnn_b200_query(const ggnn_b200_query_params* p, uint32_t N_query, ggnn_b200_stream_t stream);
 
@@ -174,6 +183,20 @@ int ggnn_b200_sym_buffer_merge(const ggnn_b200_graph_config* cfg, uint32_t layer
 int ggnn_b200_build_graph(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, float tau_build,
                           uint32_t refinement_iterations, const float* d_rng, void* d_graph_blob, void* d_scratch,
                           size_t scratch_bytes, ggnn_b200_stream_t stream);
+/* one refinement pass (GraphConstructionImpl::refine, graph_construction.cu:141-147): merge(L-1 -> layer) + sym for
+ * layer = L-2 .. 0 on a graph built before; same scratch as ggnn_b200_build_graph */
+int ggnn_b200_refine_graph(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, float tau_build,
+                           void* d_graph_blob, void* d_scratch, size_t scratch_bytes, ggnn_b200_stream_t stream);
+
+/* The reference keeps ONE cuRAND generator (XORWOW, seed 1234) per GPU whose sequence continues over all shards built on
+ * that GPU (graph_construction.cu:96-102,127).  A caller that wants the reference's selection for every shard owns such a
+ * generator and draws the uniforms of a build itself: ggnn_b200_rng_fill_build() makes the reference's three
+ * curandGenerateUniform calls (Ns[0], Ns[1], Ns[2] values, graph_construction.cu:168-169) into d_rng, which is then
+ * passed to ggnn_b200_build_graph.  (d_rng = NULL there = a fresh generator per call: right for the first shard only.) */
+typedef struct ggnn_b200_rng ggnn_b200_rng;
+int ggnn_b200_rng_create(ggnn_b200_rng** out, uint64_t seed);
+int ggnn_b200_rng_fill_build(ggnn_b200_rng* rng, const ggnn_b200_graph_config* cfg, float* d_rng, ggnn_b200_stream_t stream);
+void ggnn_b200_rng_destroy(ggnn_b200_rng* rng);
 
 /* ------------------------------------------------------------------------------------------------
  * Shard merge.  Replaces the per-GPU cub::DeviceSegmentedRadixSort (src/ggnn/base/gpu_instance.cu:745-790)

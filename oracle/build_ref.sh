@@ -31,4 +31,28 @@ if [ -f "$HERE/ref_driver.cpp" ]; then
   "$NVCC" "${FLAGS[@]}" -x cu "$HERE/ref_driver.cpp" -o "$OUT/ref_driver" \
       -L"$OUT" -lggnn_ref -lcurand -Xlinker -rpath -Xlinker '$ORIGIN'
 fi
+# The hybrid (compiled): the same unmodified reference objects, except that its two thin
+# host -> CUDA launcher files (query_kernels.cu, graph_construction.cu) are replaced by
+# integration/reference_launchers/*.cu, which call libggnn_b200.so through the C ABI.
+REPO="$(cd "$HERE/.." && pwd)"
+if [ -f "$REPO/ggnn_b200/libggnn_b200.so" ]; then
+  HOBJ="$OUT/obj_hybrid"
+  mkdir -p "$HOBJ"
+  for f in query_kernels_b200 graph_construction_b200; do
+    src="$REPO/integration/reference_launchers/$f.cu"
+    if [ ! -f "$HOBJ/$f.o" ] || [ "$src" -nt "$HOBJ/$f.o" ] || [ "$REPO/include/ggnn_b200.h" -nt "$HOBJ/$f.o" ]; then
+      "$NVCC" "${FLAGS[@]}" -I"$REPO/include" -c "$src" -o "$HOBJ/$f.o" &
+    fi
+  done
+  wait
+  REF_OBJS=$(ls "$OBJ"/*.o | grep -v -e 'query_query_kernels' -e 'construction_graph_construction')
+  "$NVCC" -shared -o "$OUT/libggnn_ref_hybrid.so" $REF_OBJS "$HOBJ"/*.o -L"$REPO/ggnn_b200" -lggnn_b200 -lcurand -lcudart \
+      -Xlinker -rpath -Xlinker '$ORIGIN/../../ggnn_b200'
+  if [ -f "$HERE/ref_driver.cpp" ]; then
+    "$NVCC" "${FLAGS[@]}" -x cu "$HERE/ref_driver.cpp" -o "$OUT/ref_driver_hybrid" \
+        -L"$OUT" -lggnn_ref_hybrid -L"$REPO/ggnn_b200" -lggnn_b200 -lcurand -Xlinker -rpath -Xlinker '$ORIGIN' \
+        -Xlinker -rpath -Xlinker '$ORIGIN/../../ggnn_b200'
+  fi
+  echo "built $OUT/libggnn_ref_hybrid.so"
+fi
 echo "built $OUT/libggnn_ref.so"
