@@ -18,7 +18,7 @@ namespace g200 {
 // bf_tc.cu
 bool tc_supported(uint32_t D, uint32_t K, int measure);
 int tc_bf_query(const ggnn_b200_bf_query_params& p, uint32_t Nq, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D);
+size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D, uint32_t K);
 
 constexpr int BF_WARPS = 8;
 constexpr int BF_QW = 4;  // queries per warp
@@ -271,7 +271,7 @@ extern "C" size_t ggnn_b200_bf_query_workspace_bytes(uint32_t D, int32_t measure
                                                      uint32_t N_query)
 {
   if (!tc_supported(D, KQuery, measure) || N_base < 128 || N_query == 0) return 0;
-  return tc_workspace_bytes(N_base, N_query, D);
+  return tc_workspace_bytes(N_base, N_query, D, KQuery);
 }
 
 extern "C" int ggnn_b200_bf_query(const ggnn_b200_bf_query_params* pin, uint32_t N_query, ggnn_b200_stream_t stream_)

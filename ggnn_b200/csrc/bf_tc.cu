@@ -38,7 +38,7 @@ constexpr int TC_BM = 128;     // queries per CTA (UMMA M)
 constexpr int TC_BN = 128;     // base rows per tile (UMMA N)
 constexpr int TC_BK = 32;      // tf32 elements per shared-memory k-block (one 128-byte swizzle row)
 constexpr int TC_STAGES = 2;   // B ring depth (each stage = hi + lo k-block = 32 KB)
-constexpr int TC_KP = 32;      // max K of the tensor path (per-row best list in shared memory)
+constexpr int TC_KP = 128;     // max K of the tensor path (per-row best lists in shared memory: 32 or 128 slots)
 constexpr int TC_THREADS = 384;  // warps 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue (2 per TMEM lane quarter)
 constexpr uint32_t TC_KBLOCK_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 
@@ -131,10 +131,13 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4])
 // UMMA descriptor expects (16-byte chunk c of row r stored at chunk c ^ (r & 7)), so the GEMM streams B with ONE
 // linear 32 KB bulk copy per stage instead of 2 x 128 strided 128-byte row segments.  Rows past n_rows are zero.
 constexpr int TC_SPLIT_ROWS = 32;  // rows per CTA of tc_split_kernel (8 warps x 4 rows)
+// normalize != 0 (cosine): every row is scaled to unit length first (zero rows stay zero) and the stored norm is
+// `unit_norm` (0 for the base, 1 for the queries): with -q/|q| as the A operand the score acc + 0 + 1 is 1 - cos(q, b),
+// the reference's cosine distance (include/ggnn/cuda_utils/distance.cuh:140-159) up to rounding far below the margin.
 __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ x, uint32_t n_rows, uint32_t n_rows_out,
                                                        uint32_t D, float scale, int tiled, float* __restrict__ hi,
                                                        float* __restrict__ lo, float* __restrict__ norms,
-                                                       unsigned int* __restrict__ max_norm_bits)
+                                                       unsigned int* __restrict__ max_norm_bits, int normalize, float unit_norm)
 {
   __shared__ float s_max[8];
   const int lane = lane_id();
@@ -155,12 +158,18 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
     float acc = fmaf(v[i].w, v[i].w, fmaf(v[i].z, v[i].z, fmaf(v[i].y, v[i].y, v[i].x * v[i].x)));
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    float row_scale = scale;
+    if (normalize) {
+      row_scale = acc > 0.f ? scale * rsqrtf(acc) : 0.f;
+      acc = unit_norm;
+    }
     if (row < n_rows) {
       if (lane == 0) norms[row] = acc;
       wmax = fmaxf(wmax, acc);
     }
     if (row < n_rows_out && act) {
-      const float4 sv = make_float4(v[i].x * scale, v[i].y * scale, v[i].z * scale, v[i].w * scale);  // power-of-two scale: exact
+      // (Euclidean: power-of-two scale, exact)
+      const float4 sv = make_float4(v[i].x * row_scale, v[i].y * row_scale, v[i].z * row_scale, v[i].w * row_scale);
       float4 h, l;
       h.x = __uint_as_float(__float_as_uint(sv.x) & 0xffffe000u);
       h.y = __uint_as_float(__float_as_uint(sv.y) & 0xffffe000u);
@@ -214,16 +223,17 @@ struct TcGemmArgs {
 constexpr int TC_STAGES_TMEM = 6;
 constexpr uint32_t TC_CHUNK = 8;
 
-template <int KB>  // k-blocks: D = 32*KB
+// KB k-blocks (D = 32*KB); KP = capacity of the per-row best lists (K <= KP); NSTAGE = depth of the B ring (the lists
+// and the ring share the shared memory: KP 32 -> 6 stages, KP 128 (the API's default KGT = 100) -> 2 stages)
+template <int KB, int KP, int NSTAGE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs a)
 {
   extern __shared__ unsigned char smem_unaligned[];
   // carve-up (every operand tile 1024-byte aligned: required by the 128-byte swizzle)
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
-  constexpr int NSTAGE = TC_STAGES_TMEM;
   unsigned char* sB = smem;                                                       // [NSTAGE][hi 16 KB | lo 16 KB]
-  float* s_kbest = reinterpret_cast<float*>(sB + NSTAGE * 2 * TC_KBLOCK_BYTES);   // [2 column halves][128][TC_KP]
-  float* s_bnorm = s_kbest + 2 * TC_BM * TC_KP;                                   // [2][128]
+  float* s_kbest = reinterpret_cast<float*>(sB + NSTAGE * 2 * TC_KBLOCK_BYTES);   // [2 column halves][128][KP]
+  float* s_bnorm = s_kbest + 2 * TC_BM * KP;                                      // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bnorm + 2 * TC_BN);
   uint64_t* full = bars;                    // [NSTAGE]
   uint64_t* empty = bars + NSTAGE;          // [NSTAGE]
@@ -368,8 +378,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
     const uint32_t q = q0 + r;
     const bool live = q < a.N_query;
     const uint32_t K = a.K;
-    float* kb = s_kbest + (ch * TC_BM + r) * TC_KP;
-    for (uint32_t i = 0; i < TC_KP; ++i) kb[i] = G200_INF;
+    float* kb = s_kbest + (ch * TC_BM + r) * KP;
+    for (uint32_t i = 0; i < KP; ++i) kb[i] = G200_INF;
     // this thread's query row (hi, lo halves of -2q) -> tensor memory lane r, one column per K element
     {
       const int half = ch;  // column-half-0 warps write the hi operand, column-half-1 warps the lo operand
@@ -554,7 +564,7 @@ struct TcRerankArgs {
   const uint32_t* cnt;
 };
 
-template <int D32>
+template <int D32, int NSK>
 __global__ void __launch_bounds__(128) tc_rerank_kernel(const TcRerankArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -579,10 +589,10 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const TcRerankArgs a)
   mbar_fence_init();
   __syncwarp();
   const ggnn_b200_bf_query_params& p = a.p;
-  const DistCfg dc{p.D, 32u, 4u, 0};
+  const DistCfg dc{p.D, 32u, 4u, p.measure};
   QueryVec<true, D32, 1> qv;
   qv.load(dc, p.d_query + static_cast<size_t>(n) * p.D, nullptr);
-  LexKBest<1> best;
+  LexKBest<NSK> best;
   best.init();
   const uint32_t K = p.KQuery;
   for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
@@ -595,16 +605,20 @@ __global__ void __launch_bounds__(128) tc_rerank_kernel(const TcRerankArgs a)
       float wd;
       int wi;
       best.worst(K, wd, wi);
-      const unsigned pm = __ballot_sync(FULL, LexKBest<1>::less(d, id, wd, wi)) & rem;
+      const unsigned pm = __ballot_sync(FULL, LexKBest<NSK>::less(d, id, wd, wi)) & rem;
       if (!pm) break;
       const int r = __ffs(pm) - 1;
       best.add(__shfl_sync(FULL, d, r), __shfl_sync(FULL, id, r));
       rem &= ~((2u << r) - 1u);
     }
   }
-  if (static_cast<uint32_t>(lane) < K) {
-    p.d_query_results[static_cast<size_t>(n) * K + lane] = best.id[0] == 0x7fffffff ? EMPTY_KEY : best.id[0];
-    if (p.d_query_results_dists) p.d_query_results_dists[static_cast<size_t>(n) * K + lane] = best.dist[0];
+#pragma unroll
+  for (int j = 0; j < NSK; ++j) {
+    const uint32_t k = 32u * j + lane;
+    if (k < K) {
+      p.d_query_results[static_cast<size_t>(n) * K + k] = best.id[j] == 0x7fffffff ? EMPTY_KEY : best.id[j];
+      if (p.d_query_results_dists) p.d_query_results_dists[static_cast<size_t>(n) * K + k] = best.dist[j];
+    }
   }
 }
 
@@ -613,6 +627,7 @@ struct KBest1 {
   int id;
   float dist;
 };
+template <int NSK>
 __global__ void __launch_bounds__(128) tc_fallback_kernel(const TcRerankArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -623,23 +638,28 @@ __global__ void __launch_bounds__(128) tc_fallback_kernel(const TcRerankArgs a)
   if (a.cnt[n] <= a.cap) return;
   const ggnn_b200_bf_query_params& p = a.p;
   float* s_q = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * p.D;
-  const DistCfg dc{p.D, 32u, 4u, 0};
+  const DistCfg dc{p.D, 32u, 4u, p.measure};
   QueryVec<false, 1, 1> qv;
   qv.load(dc, p.d_query + static_cast<size_t>(n) * p.D, s_q);
-  LexKBest<1> best;
+  LexKBest<NSK> best;
   best.init();
   const uint32_t K = p.KQuery;
   for (int i = 0; i < p.N_base; ++i) {
     float x, y;
     dist_partials_generic(dc, p.d_base + static_cast<size_t>(i) * p.D, s_q, x, y);
+    if (p.measure != 0) x = cosine_finish(x, y, qv.q_norm);
     float wd;
     int wi;
     best.worst(K, wd, wi);
-    if (LexKBest<1>::less(x, i, wd, wi)) best.add(x, i);
+    if (LexKBest<NSK>::less(x, i, wd, wi)) best.add(x, i);
   }
-  if (static_cast<uint32_t>(lane) < K) {
-    p.d_query_results[static_cast<size_t>(n) * K + lane] = best.id[0] == 0x7fffffff ? EMPTY_KEY : best.id[0];
-    if (p.d_query_results_dists) p.d_query_results_dists[static_cast<size_t>(n) * K + lane] = best.dist[0];
+#pragma unroll
+  for (int j = 0; j < NSK; ++j) {
+    const uint32_t k = 32u * j + lane;
+    if (k < K) {
+      p.d_query_results[static_cast<size_t>(n) * K + k] = best.id[j] == 0x7fffffff ? EMPTY_KEY : best.id[j];
+      if (p.d_query_results_dists) p.d_query_results_dists[static_cast<size_t>(n) * K + k] = best.dist[j];
+    }
   }
 }
 
@@ -654,7 +674,7 @@ struct TcWorkspace {
   size_t total;
 };
 constexpr uint32_t TC_MAX_SPLITS = 32;  // 64 published best lists per query
-static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, uint32_t cap)
+static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, uint32_t cap, uint32_t K)
 {
   char* b = static_cast<char*>(basep);
   size_t off = 0;
@@ -674,7 +694,7 @@ static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, u
   w.max_norm = reinterpret_cast<unsigned int*>(take(1024));
   w.cnt = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(Nq) * 4));
   w.tau_g = reinterpret_cast<unsigned int*>(take(static_cast<size_t>(Nq) * 4));
-  w.pub = reinterpret_cast<unsigned int*>(take(static_cast<size_t>(Nq) * 2 * TC_MAX_SPLITS * TC_KP * 4));
+  w.pub = reinterpret_cast<unsigned int*>(take(static_cast<size_t>(Nq) * 2 * TC_MAX_SPLITS * K * 4));
   w.cand = reinterpret_cast<int32_t*>(take(static_cast<size_t>(Nq) * cap * 4));
   w.total = off;
   return w;
@@ -693,10 +713,11 @@ static uint32_t tc_cap(uint32_t Nq)
 }
 
 // number of base splits: fill the SMs (one 209 KB CTA each) in whole waves, within the candidate capacity
-static uint32_t tc_pick_splits(uint32_t q_tiles, uint32_t n_tiles, uint32_t num_sms, uint32_t cap)
+static uint32_t tc_pick_splits(uint32_t q_tiles, uint32_t n_tiles, uint32_t num_sms, uint32_t cap, uint32_t K)
 {
   const uint32_t forced = env_u32("GGNN_B200_BF_SPLITS", 0);
-  const uint32_t s_max = std::max(1u, std::min(std::min(n_tiles, TC_MAX_SPLITS), cap / TC_CAND_PER_SPLIT));
+  const uint32_t per_split = std::max(TC_CAND_PER_SPLIT, 20u * K);  // ~2 lists x K (1 + ln(rows / K)) per split
+  const uint32_t s_max = std::max(1u, std::min(std::min(n_tiles, TC_MAX_SPLITS), cap / per_split));
   if (forced) return std::max(1u, std::min(std::min(forced, TC_MAX_SPLITS), n_tiles));
   uint32_t best = 1;
   double best_score = -1.0;
@@ -716,10 +737,11 @@ static uint32_t tc_pick_splits(uint32_t q_tiles, uint32_t n_tiles, uint32_t num_
 
 bool tc_supported(uint32_t D, uint32_t K, int measure)
 {
-  return measure == GGNN_B200_EUCLIDEAN && D % 32 == 0 && D >= 32 && D <= 128 && K >= 1 && K <= TC_KP;
+  return (measure == GGNN_B200_EUCLIDEAN || measure == GGNN_B200_COSINE) && D % 32 == 0 && D >= 32 && D <= 128 && K >= 1 &&
+         K <= TC_KP;
 }
 
-template <int KB>
+template <int KB, int KP, int NSTAGE>
 static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorkspace& w, cudaStream_t stream)
 {
   const uint32_t N = static_cast<uint32_t>(p.N_base), D = p.D;
@@ -729,14 +751,18 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   if ((e = cudaMemsetAsync(w.cnt, 0, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset cnt");
   if ((e = cudaMemsetAsync(w.tau_g, 0x7f, static_cast<size_t>(Nq) * 4, stream)) != cudaSuccess) return set_cuda_error(e, "memset tau");  // 0x7f7f7f7f = 3.4e38
   const uint32_t N_pad = (N + TC_BN - 1) / TC_BN * TC_BN;
-  tc_split_kernel<<<(N_pad + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, 256, 0, stream>>>(p.d_base, N, N_pad, D, 1.0f, 1, w.b_hi, nullptr, w.bnorm, w.max_norm);
-  tc_split_kernel<<<(Nq + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, 256, 0, stream>>>(p.d_query, Nq, Nq, D, -2.0f, 0, w.q_hi, w.q_lo, w.qnorm, nullptr);
+  const int cosine = p.measure == GGNN_B200_COSINE;
+  // Euclidean: |b|^2 + (-2q).b + |q|^2.  Cosine: unit rows, 0 + (-q/|q|).(b/|b|) + 1 = 1 - cos
+  tc_split_kernel<<<(N_pad + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, 256, 0, stream>>>(p.d_base, N, N_pad, D, 1.0f, 1, w.b_hi, nullptr, w.bnorm,
+                                                                                    w.max_norm, cosine, 0.0f);
+  tc_split_kernel<<<(Nq + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, 256, 0, stream>>>(p.d_query, Nq, Nq, D, cosine ? -1.0f : -2.0f, 0, w.q_hi,
+                                                                                 w.q_lo, w.qnorm, nullptr, cosine, 1.0f);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_split_kernel launch");
 
   const DeviceInfo& dev = device_info();
   const uint32_t q_tiles = (Nq + TC_BM - 1) / TC_BM;
   const uint32_t n_tiles = (N + TC_BN - 1) / TC_BN;
-  const uint32_t splits = tc_pick_splits(q_tiles, n_tiles, dev.num_sms, cap);
+  const uint32_t splits = tc_pick_splits(q_tiles, n_tiles, dev.num_sms, cap, p.KQuery);
   const uint32_t tiles_per_split = (n_tiles + splits - 1) / splits;
 
   TcGemmArgs ga{};
@@ -758,8 +784,8 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ga.q_lo = w.q_lo;
   ga.b_tiled = w.b_hi;
   ga.D = D;
-  const size_t smem = static_cast<size_t>(TC_STAGES_TMEM) * 2 * TC_KBLOCK_BYTES + 2 * TC_BM * TC_KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
-  auto gemm = tc_gemm_kernel<KB>;
+  const size_t smem = static_cast<size_t>(NSTAGE) * 2 * TC_KBLOCK_BYTES + 2 * TC_BM * KP * 4 + 2 * TC_BN * 4 + 256 + 1024;
+  auto gemm = tc_gemm_kernel<KB, KP, NSTAGE>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
   gemm<<<dim3(q_tiles, splits), TC_THREADS, smem, stream>>>(ga);
@@ -773,11 +799,11 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   ra.cnt = w.cnt;
   ra.warp_smem_bytes = align_up(32 * D * 4 + 32, 128);
   const size_t rsmem = static_cast<size_t>(ra.warp_smem_bytes) * 4;
-  auto rr = tc_rerank_kernel<KB>;
+  auto rr = tc_rerank_kernel<KB, KP / 32>;
   if ((e = cudaFuncSetAttribute(rr, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(tc_rerank_kernel)");
   rr<<<(Nq + 3) / 4, 128, rsmem, stream>>>(ra);
-  tc_fallback_kernel<<<(Nq + 3) / 4, 128, 4 * D * 4, stream>>>(ra);
+  tc_fallback_kernel<KP / 32><<<(Nq + 3) / 4, 128, 4 * D * 4, stream>>>(ra);
   if (env_u32("GGNN_B200_BF_DEBUG", 0)) {  // diagnostics only: candidate slots handed out per query
     std::vector<uint32_t> h(Nq);
     cudaStreamSynchronize(stream);
@@ -797,17 +823,18 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
 
 int tc_bf_query(const ggnn_b200_bf_query_params& p, uint32_t Nq, void* workspace, size_t workspace_bytes, cudaStream_t stream)
 {
-  const TcWorkspace w = tc_layout(workspace, static_cast<uint32_t>(p.N_base), Nq, p.D, tc_cap(Nq));
+  const TcWorkspace w = tc_layout(workspace, static_cast<uint32_t>(p.N_base), Nq, p.D, tc_cap(Nq), p.KQuery);
   if (workspace_bytes < w.total) return set_error(GGNN_B200_ERR_INVALID, "bf_query workspace too small");
+  const bool small_k = p.KQuery <= 32;
   switch (p.D / 32) {
-    case 1: return tc_run<1>(p, Nq, w, stream);
-    case 2: return tc_run<2>(p, Nq, w, stream);
-    case 3: return tc_run<3>(p, Nq, w, stream);
-    case 4: return tc_run<4>(p, Nq, w, stream);
+    case 1: return small_k ? tc_run<1, 32, 6>(p, Nq, w, stream) : tc_run<1, 128, 2>(p, Nq, w, stream);
+    case 2: return small_k ? tc_run<2, 32, 6>(p, Nq, w, stream) : tc_run<2, 128, 2>(p, Nq, w, stream);
+    case 3: return small_k ? tc_run<3, 32, 6>(p, Nq, w, stream) : tc_run<3, 128, 2>(p, Nq, w, stream);
+    case 4: return small_k ? tc_run<4, 32, 6>(p, Nq, w, stream) : tc_run<4, 128, 2>(p, Nq, w, stream);
   }
   return set_error(GGNN_B200_ERR_UNSUPPORTED, "tensor-core bf_query needs D in {32, 64, 96, 128}");
 }
 
-size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D) { return tc_layout(nullptr, N, Nq, D, tc_cap(Nq)).total; }
+size_t tc_workspace_bytes(uint32_t N, uint32_t Nq, uint32_t D, uint32_t K) { return tc_layout(nullptr, N, Nq, D, tc_cap(Nq), K).total; }
 
 }  // namespace g200

@@ -17,6 +17,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// experiment switches of the push path (all on by default; none changes results -- see tools/ab_query.py)
+#ifndef G200_OPT_FLAGS
+#define G200_OPT_FLAGS 1     // per-lane slot predicates of push() hoisted into a flag word
+#endif
+#ifndef G200_OPT_DUPSKIP
+#define G200_OPT_DUPSKIP 0   // duplicate check only for within-fetch duplicates (found with MATCH.ANY): measured SLOWER
+#endif                       // (0.566 vs 0.544 ms per batch) -- the match sits on the serial chain of the traversal
+#ifndef G200_OPT_LAZYCRIT
+#define G200_OPT_LAZYCRIT 1  // criteria() re-read only after a push that changed the best list
+#endif
+
 namespace g200 {
 
 constexpr int EMPTY_KEY = -1;
@@ -415,7 +426,12 @@ struct WarpLists {
       }
       // slot p receives old[p-1] iff p-1 is active and non-empty and p is neither the start of the
       // best list / prioQ region nor the ring head (:166-172; idx_next==BEST swallows the ring wrap)
+#if G200_OPT_FLAGS
       const bool recv = ((lane_flags >> (3 * j)) & 1u) && (pd >= d) && (pk != EMPTY_KEY);
+#else
+      const uint32_t p = 32u * j + lane;
+      const bool recv = (p >= 1) && (p != BEST) && (p != head) && (pd >= d) && (pk != EMPTY_KEY);
+#endif
       asd[j] = recv ? pd : dist[j];
       nk[j] = recv ? pk : key[j];
     }
@@ -427,9 +443,16 @@ struct WarpLists {
         const float ca = __shfl_sync(FULL, asd[j - 1], 31);
         if (lane == 0) pa = ca;
       }
+#if G200_OPT_FLAGS
       if ((lane_flags >> (3 * j)) & 4u) pa = last_asd;  // p == BEST: idx_prev = SORTED-1 (:177)
       const bool active = dist[j] >= d;
       const bool has_prev = (lane_flags >> (3 * j)) & 2u;
+#else
+      const uint32_t p = 32u * j + lane;
+      if (p == BEST) pa = last_asd;
+      const bool active = dist[j] >= d;
+      const bool has_prev = (p != 0) && (p != head);
+#endif
       const bool ins = active && (!has_prev || pa < d);  // :176-182
       key[j] = ins ? k : nk[j];
       dist[j] = ins ? d : asd[j];

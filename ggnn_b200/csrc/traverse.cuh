@@ -288,7 +288,7 @@ __device__ __forceinline__ void finish_fetch(LT& L, int key_r, float mine, int c
   // duplicates WITHIN this fetch (a graph row may name a point twice): only those can already be in the lists when
   // their turn comes -- every other candidate passed the filter and nothing but its fellow candidates is pushed before it
   unsigned dupmask = FULL;
-  if constexpr (FILTER) {
+  if constexpr (FILTER && G200_OPT_DUPSKIP) {
     const unsigned same = __match_any_sync(FULL, lane < cnt ? key_r : (-2 - lane));
     dupmask = __ballot_sync(FULL, (same & ((1u << lane) - 1u)) != 0u);
   }
@@ -329,7 +329,7 @@ __device__ __forceinline__ void finish_fetch(LT& L, int key_r, float mine, int c
     const float d = __shfl_sync(FULL, mine, c0);
     L.push(k, d, (dupmask >> c0) & 1u);
     pm &= pm - 1u;
-    if (d < best_last) {
+    if (!G200_OPT_LAZYCRIT || d < best_last) {
       best_last = L.dist_at(L.BEST - 1);
       pm &= __ballot_sync(FULL, mine < best_last + xi);
     }

@@ -97,21 +97,27 @@ def test_bf_query_matches_reference_dump(golden, name):
     assert np.array_equal(ids, g["bf_ids"]) and np.array_equal(dists, g["bf_dists"])
 
 
-@pytest.mark.parametrize("N,Nq,D,K,kind", [(3000, 70, 128, 10, "uniform"), (1000, 300, 64, 32, "uniform"),
-                                           (2500, 129, 96, 1, "normal"), (333, 5, 32, 10, "uniform"),
-                                           (40000, 257, 128, 10, "uniform")])
-def test_bf_query_tensor_core_path_bit_exact_vs_oracle(N, Nq, D, K, kind):
+@pytest.mark.parametrize("N,Nq,D,K,kind,measure", [(3000, 70, 128, 10, "uniform", 0), (1000, 300, 64, 32, "uniform", 0),
+                                                   (2500, 129, 96, 1, "normal", 0), (333, 5, 32, 10, "uniform", 0),
+                                                   (40000, 257, 128, 10, "uniform", 0),
+                                                   (20000, 200, 128, 100, "uniform", 0),   # the API's default KGT = 100
+                                                   (5000, 130, 96, 128, "normal", 0), (3000, 70, 96, 10, "normal", 1),
+                                                   (20000, 257, 96, 100, "normal", 1), (2000, 64, 128, 33, "uniform", 1)])
+def test_bf_query_tensor_core_path_bit_exact_vs_oracle(N, Nq, D, K, kind, measure):
     """tcgen05 3xTF32 contraction -> candidate lists -> exact re-rank: same ids AND distances as the reference
-    arithmetic (oracle), including exact ties (duplicate rows) and ragged tile edges"""
+    arithmetic (oracle), including exact ties (duplicate rows) and ragged tile edges; Euclidean and cosine
+    (unit-normalised operands), K up to 128 (include/ggnn/base/ggnn.cuh:166 defaults to KGT = 100)"""
     base, query = gen_data(N, Nq, D, seed=N + D, kind=kind)
     base[5] = base[3]
     base[N - 1] = base[0]
     query[0] = base[3]  # distance 0 twice
-    ids, dists = c_bf(base, query, K, 0, tensor_cores=True)
-    nq_o = min(Nq, 64)
-    o_ids, o_d = O.bf_query(base, query[:nq_o], K, 0)
+    if measure:
+        base[7] = 0.0   # a zero vector: cosine distance 1 by definition (distance.cuh:153-158)
+    ids, dists = c_bf(base, query, K, measure, tensor_cores=True)
+    nq_o = min(Nq, 64 if K <= 32 else 16)
+    o_ids, o_d = O.bf_query(base, query[:nq_o], K, measure)
     assert np.array_equal(ids[:nq_o], o_ids) and np.array_equal(dists[:nq_o], o_d)
-    e_ids, e_d = c_bf(base, query, K, 0)  # all queries vs the exact SIMT scan
+    e_ids, e_d = c_bf(base, query, K, measure)  # all queries vs the exact SIMT scan
     assert np.array_equal(ids, e_ids) and np.array_equal(dists, e_d)
 
 
@@ -914,7 +920,7 @@ def test_reference_with_our_launchers_is_bit_identical(tmp_path):
                (("query_ids", np.int32), ("query_dists", np.float32), ("bf_ids", np.int32), ("bf_dists", np.float32))}
         return out, json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
 
-    for shard in (0, N // 2):            # one shard; two shards on the GPU (reference's interleaved buffer + segmented sort)
+    for shard in (N // 2, 0):            # two shards on the GPU (reference's interleaved buffer + segmented sort); one shard
         kw = {"shard": shard} if shard else {}
         r, _ = run(ref, build=1, **kw)   # the reference builds and stores part_*.ggnn, then answers
         h, _ = run(hyb, build=0, **kw)   # the reference's GGNN / GPUInstance load the same files, OUR kernels answer
@@ -934,7 +940,7 @@ def test_reference_with_our_launchers_is_bit_identical(tmp_path):
 # native uint8 rows
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("D,measure,K,max_it", [(128, 0, 10, 400), (96, 0, 10, 400), (256, 0, 10, 200), (160, 1, 10, 400),
-                                                (128, 1, 32, 200), (64, 0, 1, 400), (16, 0, 10, 400)])
+                                                (128, 1, 32, 200), (64, 0, 1, 400), (32, 0, 10, 400)])
 def test_native_uint8_query_kernel_bit_exact_vs_oracle(D, measure, K, max_it):
     """query_kernel_u8 (1-byte rows staged by TMA gather4, integer dp4a distances, one REDUX per row) through the C ABI
     with base_type = GGNN_B200_BASE_U8 against the oracle on the widened values: ids, distances AND the pop / distance
