@@ -618,6 +618,30 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s):
             ev[2 * r + 1].record()
         torch.cuda.synchronize()
         return out, float(np.mean([ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps)]))
+    # config 1: the README example -- 10 000 x 128 uniform base and 10 000 queries as CPU-resident tensors, everything
+    # (host -> device copies, results back to the host) inside the timed call
+    try:
+        bc, qc = config1_data()
+        c1 = ggnn.GGNN()
+        c1.set_base(bc)
+        t0 = time.perf_counter()
+        c1.build(a.k_build, a.tau_build, a.refine)
+        torch.cuda.synchronize()
+        c1_build = time.perf_counter() - t0
+        c1.query(qc, K, a.tau_query, a.max_iterations)
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            ci, _ = c1.query(qc, K, a.tau_query, a.max_iterations)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        cg, _ = c1.bf_query(qc, K)
+        ex["config1"] = {"workload": "README example: 10000x128 U[0,1) fp32 base + 10000 queries as CPU tensors (torch.manual_seed(1234)), "
+                                     f"k_build={a.k_build} tau_build={a.tau_build}, k_query={K} tau_query={a.tau_query} max_iterations={a.max_iterations}",
+                         "build_s": c1_build, "query_ms_host_to_host": float(np.median(ts)), "queries_per_s": 10_000 / (float(np.median(ts)) * 1e-3),
+                         "recall_at_10": recall_at_k(cg, ci, K), "bf_ids_crc32": _crc(cg)}
+        del c1
+    except Exception as e:  # noqa: BLE001
+        ex["config1"] = {"error": repr(e)[-300:]}
     # config 5: bf_query 1M x 10k as a tensor-core contraction (+ exact re-rank), k = 10 and the API default k = 100
     try:
         (bi, bd), ms10 = timed(lambda: idx.bf_query(query, K))
@@ -716,6 +740,12 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s):
     except Exception as e:  # noqa: BLE001
         ex["config3"] = {"error": repr(e)[-300:]}
     return ex
+
+
+def config1_data():
+    """BASELINE config 1 (README.md:94-95 of the reference): torch.rand on the CPU, base first, then the queries"""
+    g = torch.Generator().manual_seed(1234)
+    return torch.rand((10_000, 128), generator=g), torch.rand((10_000, 128), generator=g)
 
 
 def load_profile_note(name):
@@ -854,6 +884,27 @@ def run_reference(a):
         pass
     for f in os.listdir(wd):
         os.remove(os.path.join(wd, f))
+    config1 = None
+    if shards == 1:  # BASELINE config 1 through the reference's API (same tensors as our arm's extra.config1)
+        try:
+            bc, qc = config1_data()
+            bc.numpy().tofile(os.path.join(wd, "base.bin"))
+            qc.numpy().tofile(os.path.join(wd, "query.bin"))
+            p1 = subprocess.run([drv, f"dir={wd}", "n=10000", "nq=10000", "d=128", "measure=0", f"kbuild={a.k_build}",
+                                 f"tau_build={a.tau_build}", f"refine={a.refine}", "build=1", f"kquery={a.k_query}",
+                                 f"tau_query={a.tau_query}", f"max_iter={a.max_iterations}", "query_reps=11", "gpu_reps=0",
+                                 f"bf={a.k_query}", "dump=1"], capture_output=True, text=True)
+            r1 = json.loads([l for l in p1.stdout.splitlines() if l.startswith("{")][-1])
+            i1 = np.fromfile(os.path.join(wd, "query_ids.bin"), np.int32).reshape(10000, a.k_query)
+            g1 = np.fromfile(os.path.join(wd, "bf_ids.bin"), np.int32).reshape(10000, a.k_query)
+            config1 = {"build_s": r1.get("build_s"), "query_ms_host_to_host": float(np.median(r1["query_e2e_ms"][1:])),
+                       "kernel_ms": float(np.median(r1["query_kernel_ms"][1:])) if r1.get("query_kernel_ms") else None,
+                       "recall_at_10": recall_at_k(torch.from_numpy(g1), torch.from_numpy(i1), a.k_query),
+                       "bf_ids_crc32": zlib.crc32(g1.tobytes()) & 0xffffffff}
+            for f in os.listdir(wd):
+                os.remove(os.path.join(wd, f))
+        except Exception as e:  # noqa: BLE001
+            config1 = {"error": repr(e)[-300:]}
     ms_step = float(np.sum(kern)) / a.steps
     e2e_step = float(np.sum(e2e)) / a.steps
     q_per_step = Nq * B
@@ -873,7 +924,7 @@ def run_reference(a):
                    "reference_build_s": r.get("build_s"), "reference_build_s_earlier_in_process": r.get("build_s_all"),
                    "reference_kernel_ms_per_batch": float(np.mean(kern)),
                    "reference_wall_ms_per_batch_results_on_gpu": float(np.mean(wall_gpu[skip:])) if wall_gpu else None,
-                   "bf_ids_crc32_k10": bf_crc, "bf_s": r.get("bf_s")},
+                   "bf_ids_crc32_k10": bf_crc, "bf_s": r.get("bf_s"), "config1": config1},
         "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "mode": "wall clock around one synchronous ggnn::GGNN::query() per batch, pinned host query, results to the host"},
         "cpu_baseline": {"value": e2e_val, "unit": unit, "kind": "reference", "cores": shards,

@@ -237,6 +237,61 @@ __global__ void __launch_bounds__(BF_WARPS * 32) bf_kernel_generic(const BfArgs 
   }
 }
 
+// ---- any K (129 .. 6000, src/ggnn/query/query_kernels.cu:204-218): the K-best list lives in shared memory ----
+// One warp per query; the list is kept sorted by KBestList::add_unique's rule (k_best_list.cuh:77-109: entries with a
+// larger distance move right, the new entry goes after all entries with dist <= d), 32 slots per step from the right.
+constexpr int BF_BIGK_WARPS = 4;
+__global__ void __launch_bounds__(BF_BIGK_WARPS * 32) bf_kernel_bigk(const BfArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const ggnn_b200_bf_query_params& p = a.p;
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t n = blockIdx.x * BF_BIGK_WARPS + warp;
+  if (n >= a.N_query) return;
+  const uint32_t K = p.KQuery;
+  float* s_q = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * p.D;
+  float* l_d = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(BF_BIGK_WARPS) * p.D + static_cast<size_t>(warp) * 2 * K;
+  int* l_i = reinterpret_cast<int*>(l_d + K);
+  const DistCfg dc{p.D, a.block_dim_x, 4u, p.measure};
+  QueryVec<false, 1, 1> qv;
+  qv.load(dc, p.d_query + static_cast<size_t>(n) * p.D, s_q);
+  for (uint32_t k = lane; k < K; k += 32) {
+    l_d[k] = G200_INF;
+    l_i[k] = EMPTY_KEY;
+  }
+  __syncwarp();
+  for (int i = 0; i < p.N_base; ++i) {
+    float x, y;
+    dist_partials_generic(dc, p.d_base + static_cast<size_t>(i) * p.D, s_q, x, y);
+    const float d = p.measure == 0 ? x : cosine_finish(x, y, qv.q_norm);
+    if (!(d < l_d[K - 1])) continue;
+    uint32_t pos = 0;
+    for (int b = static_cast<int>((K - 1) / 32 * 32); b >= 0; b -= 32) {
+      const uint32_t k = b + lane;
+      const bool in = k < K;
+      const float od = in ? l_d[k] : 0.f;
+      const int oi = in ? l_i[k] : 0;
+      __syncwarp();
+      if (in && d < od && k + 1 < K) {
+        l_d[k + 1] = od;
+        l_i[k + 1] = oi;
+      }
+      pos += __popc(__ballot_sync(FULL, in && od <= d));
+      __syncwarp();
+    }
+    if (lane == 0) {
+      l_d[pos] = d;
+      l_i[pos] = i;
+    }
+    __syncwarp();
+  }
+  for (uint32_t k = lane; k < K; k += 32) {
+    p.d_query_results[static_cast<size_t>(n) * K + k] = l_i[k];
+    if (p.d_query_results_dists) p.d_query_results_dists[static_cast<size_t>(n) * K + k] = l_d[k];
+  }
+}
+
 template <int NI, int NSK>
 static int launch_fast(const BfArgs& a, cudaStream_t stream)
 {
@@ -294,7 +349,14 @@ extern "C" int ggnn_b200_bf_query(const ggnn_b200_bf_query_params* pin, uint32_t
   a.N_query = N_query;
   a.block_dim_x = std::max(32u, bit_ceil_u32((p.D + 3) / 4));
   const int NSK = (p.KQuery + 31) / 32;
-  if (NSK > 4) return set_error(GGNN_B200_ERR_UNSUPPORTED, "KQuery > 128 not built yet for bf_query");
+  if (NSK > 4) {  // up to the reference's MAX_K_QUERY = 6000: list in shared memory
+    const size_t smem = static_cast<size_t>(BF_BIGK_WARPS) * (p.D * 4 + static_cast<size_t>(p.KQuery) * 8);
+    if (smem > device_info().smem_per_block_optin) return set_error(GGNN_B200_ERR_UNSUPPORTED, "bf_query: KQuery * D too large for shared memory");
+    cudaError_t e = cudaFuncSetAttribute(bf_kernel_bigk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(bf_kernel_bigk)");
+    bf_kernel_bigk<<<(N_query + BF_BIGK_WARPS - 1) / BF_BIGK_WARPS, BF_BIGK_WARPS * 32, smem, stream>>>(a);
+    return set_cuda_error(cudaGetLastError(), "bf_kernel_bigk launch");
+  }
   const bool fast = (p.D % 32 == 0) && (p.D <= 128);
   if (fast) {
     a.tile_rows = env_u32("GGNN_B200_BF_TILE_ROWS", 64);

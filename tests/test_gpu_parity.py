@@ -90,6 +90,18 @@ def test_bf_query_bit_exact_vs_oracle(N, Nq, D, K, measure, kind):
     assert np.array_equal(dists, o_d)
 
 
+@pytest.mark.parametrize("N,Nq,D,K,measure", [(3000, 20, 64, 200, 0), (7000, 9, 128, 1000, 0), (6500, 5, 96, 6000, 1),
+                                               (2000, 12, 50, 129, 0)])
+def test_bf_query_large_k_bit_exact_vs_oracle(N, Nq, D, K, measure):
+    """KQuery up to the reference's MAX_K_QUERY = 6000 (src/ggnn/query/query_kernels.cu:204-218): list in shared memory"""
+    base, query = gen_data(N, Nq, D, seed=K, kind="normal" if measure else "uniform")
+    base[5] = base[3]
+    query[0] = base[3]
+    ids, dists = c_bf(base, query, K, measure)
+    o_ids, o_d = O.bf_query(base, query, K, measure)
+    assert np.array_equal(ids, o_ids) and np.array_equal(dists, o_d)
+
+
 @pytest.mark.parametrize("name", ["l2_10k", "cos_10k"])
 def test_bf_query_matches_reference_dump(golden, name):
     g = golden[name]
@@ -1000,3 +1012,26 @@ def test_native_uint8_api_paths_agree(monkeypatch):
     assert torch.equal(i1, i2) and torch.equal(d1, d2)
     gt, _ = g.bf_query(q, 10)
     assert ggnn.Evaluator(None, None, gt, 10).evaluate_results(i1).c_k_query > 0.5
+
+
+def test_gpu_resident_tensors_are_used_in_place():
+    """a CUDA base tensor is not copied (the reference clones every input, nanobind.cu:102-110), CUDA
+    queries are read where they are, and with set_return_results_on_gpu the results never leave the device"""
+    base, query = gen_data(20000, 1000, 64, seed=13)
+    b, q = torch.from_numpy(base).cuda(), torch.from_numpy(query).cuda()
+    g = ggnn.GGNN()
+    g.set_return_results_on_gpu(True)
+    g.set_base(b)
+    g.build(24, 0.5)
+    assert g._shards[0].base.data_ptr() == b.data_ptr()            # the user's tensor IS the shard
+    before = torch.cuda.memory_allocated()
+    ids, dists = g.query(q, 10, 0.6, 200)
+    assert ids.is_cuda and dists.is_cuda
+    torch.cuda.synchronize()
+    # only the two result tensors (+ allocator rounding) were allocated: no copy of the 1000 x 64 query batch
+    assert torch.cuda.memory_allocated() - before <= 2 * (1000 * 10 * 4 + 512) + 2048
+    gs = ggnn.GGNN()                                               # two shards of one CUDA tensor: views, no copies
+    gs.set_shard_size(10000)
+    gs.set_base(b)
+    gs._prepare(24)
+    assert [sh.base.data_ptr() for sh in gs._shards] == [b.data_ptr(), b[10000:].data_ptr()]
