@@ -236,16 +236,33 @@ def run_ours(a):
     idx.build(a.k_build, a.tau_build, a.refine)
     torch.cuda.synchronize()
     build_s = time.time() - t0
-    build_warm_s = None
+    build_warm_s, build_passes = None, None
     if world == 1:  # the first build of a process pays module load / context set-up: time a second one (fresh object)
+        from ggnn_b200 import _lib
         tmp = ggnn.GGNN()
         tmp.set_gpus([local])
         tmp.set_base(base)
         torch.cuda.synchronize()
+        _lib.check(_lib.lib().ggnn_b200_build_stats_begin())   # per-launch counters + event times of merge / sym
         t0 = time.time()
         tmp.build(a.k_build, a.tau_build, a.refine)
         torch.cuda.synchronize()
         build_warm_s = time.time() - t0
+        ps = (_lib.BuildPassStats * 64)()
+        n_ps = C.c_uint32(0)
+        _lib.check(_lib.lib().ggnn_b200_build_stats_end(ps, 64, C.byref(n_ps)))
+        build_passes = []
+        peak_b, _ = measured_peaks()
+        for i in range(n_ps.value):
+            s_ = ps[i]
+            if s_.layer_btm != 0:
+                continue   # (the upper layers are 3 % of the build)
+            # algorithmic bytes: 4*D per point read + 4*D per distance evaluation (sym: one row read serves
+            # both of its distances) + 4*KBuild per pop
+            alg = 4.0 * a.dim * (s_.points + s_.dists) + 4.0 * a.k_build * s_.pops
+            build_passes.append({"kernel": "sym" if s_.kernel else "merge", "layer_top": s_.layer_top, "ms": s_.ms,
+                                 "pops_per_point": s_.pops / s_.points, "dists_per_point": s_.dists / s_.points,
+                                 "algorithmic_gbs": alg / (s_.ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (s_.ms * 1e-3) / 1e9 / peak_b})
         del tmp
 
     def local_query(q):
@@ -448,7 +465,7 @@ def run_ours(a):
     cpu = cpu_baseline(a, idx, base, query, gr)
     extra = None
     if world == 1 and a.extras:
-        extra = run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s)
+        extra = run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes)
     out = {
         "metric": "queries/sec @ recall@10", "value": qps * shards, "unit": "queries/s" if shards == 1 else "queries/s x shards searched",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -601,12 +618,13 @@ def run_config4(a, dev, world, rank, local):
     return out
 
 
-def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s):
+def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes=None):
     """N = 1 only, untimed by the headline: the other BASELINE configs on the same box"""
     import ggnn_b200 as ggnn
     K, Nq = a.k_query, a.n_query
     ex = {"build": {"first_in_process_s": build_s, "warm_s": build_warm_s,
-                    "what": f"{a.n_base}x{a.dim} k_build={a.k_build} tau_build={a.tau_build} refine={a.refine}"}}
+                    "what": f"{a.n_base}x{a.dim} k_build={a.k_build} tau_build={a.tau_build} refine={a.refine}",
+                    "layer0_passes": build_passes}}
 
     def timed(fn, reps=3):
         fn()

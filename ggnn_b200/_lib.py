@@ -54,6 +54,11 @@ class BfQueryParams(C.Structure):
     ]
 
 
+class BuildPassStats(C.Structure):
+    _fields_ = [("kernel", C.c_uint32), ("layer_top", C.c_uint32), ("layer_btm", C.c_uint32), ("points", C.c_uint32),
+                ("pops", C.c_uint64), ("dists", C.c_uint64), ("ms", C.c_float)]
+
+
 EXPORTS = [
     "ggnn_b200_last_error", "ggnn_b200_version", "ggnn_b200_graph_config_init", "ggnn_b200_graph_blob_bytes",
     "ggnn_b200_graph_blob_offsets", "ggnn_b200_build_scratch_bytes", "ggnn_b200_query_shape_init",
@@ -62,6 +67,7 @@ EXPORTS = [
     "ggnn_b200_merge_topk", "ggnn_b200_widen_u8",
     "ggnn_b200_ipc_alloc", "ggnn_b200_ipc_open", "ggnn_b200_ipc_close", "ggnn_b200_ipc_free", "ggnn_b200_peer_enable",
     "ggnn_b200_wait_flag", "ggnn_b200_refine_graph", "ggnn_b200_rng_create", "ggnn_b200_rng_fill_build", "ggnn_b200_rng_destroy",
+    "ggnn_b200_build_stats_begin", "ggnn_b200_build_stats_end",
 ]
 
 _lib = None
@@ -114,6 +120,8 @@ def lib():
         l.ggnn_b200_rng_fill_build.argtypes = [vp, cfgp, vp, vp]
         l.ggnn_b200_rng_destroy.argtypes = [vp]
         l.ggnn_b200_rng_destroy.restype = None
+        l.ggnn_b200_build_stats_begin.argtypes = []
+        l.ggnn_b200_build_stats_end.argtypes = [C.POINTER(BuildPassStats), u32, C.POINTER(u32)]
         _lib = l
     return _lib
 

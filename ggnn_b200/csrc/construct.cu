@@ -361,6 +361,7 @@ struct MergeArgs {
   uint32_t sorted, cache, max_iterations;
   WarpPlan pl;
   int32_t pad_row;        // gather4 staging (see traverse.cuh)
+  unsigned long long* counters;  // optional {pops, distance evaluations, points} of this launch (diagnostics)
   TensorMapStorage tmap;  // tensor map of the base for the gather4 variants
 };
 
@@ -408,8 +409,14 @@ __device__ __forceinline__ void lists_transform(WarpLists<NS>& L, const int32_t*
   L.update_flags();
 }
 
+#ifndef G200_MERGE_MB
+#define G200_MERGE_MB 5  // resident CTAs per SM the gather4 variants are compiled for (register cap)
+#endif
+#ifndef G200_SYM_MB
+#define G200_SYM_MB 1
+#endif
 template <int NS, bool FAST, int D32, int NW, bool G4 = false>
-__global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid_constant__ MergeArgs a)
+__global__ void __launch_bounds__(CW * 32, G4 ? G200_MERGE_MB : 1) merge_kernel(const __grid_constant__ MergeArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
@@ -426,6 +433,7 @@ __global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid
   const float mean_nn1 = a.nn1_stats[0];
   const float xi = (a.measure == 0) ? __fmul_rn(__fmul_rn(__fmul_rn(mean_nn1, mean_nn1), a.tau_build), a.tau_build)
                                     : __fmul_rn(mean_nn1, a.tau_build);
+  unsigned long long tot_pops = 0, tot_dists = 0, tot_points = 0;
   // persistent warps: warp w of the grid handles points w, w + W, w + 2W, ... -- a warp slot is never held idle by the
   // slower warps of its CTA, and at any time the resident warps work on one contiguous block of points (L2 locality)
   for (uint32_t n = blockIdx.x * CW + warp; n < a.N_btm; n += gridDim.x * CW) {
@@ -469,6 +477,7 @@ __global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid
       const int anchor = L.pop(crit);
       if (anchor == EMPTY_KEY) break;
       V.insert(anchor);
+      st.pops++;
       for (uint32_t j = 0; j < K; j += 32) {
         int ck;
         if (use_spec && spec.key == anchor) ck = spec.row;  // speculative load issued before the previous push loop
@@ -519,7 +528,15 @@ __global__ void __launch_bounds__(CW * 32, G4 ? 5 : 1) merge_kernel(const __grid
     if (lane == 0) a.nn1[n] = dist;
   }
   __syncwarp();
+  tot_pops += st.pops;
+  tot_dists += st.dists;
+  ++tot_points;
   }  // points of this warp
+  if (a.counters && lane == 0) {
+    atomicAdd(&a.counters[0], tot_pops);
+    atomicAdd(&a.counters[1], tot_dists);
+    atomicAdd(&a.counters[2], tot_points);
+  }
 }
 
 // ================================================================================================
@@ -539,6 +556,7 @@ struct SymArgs {
   WarpPlan pl;
   int32_t pad_row;        // gather4 staging (see traverse.cuh); stage_mode 3 in `pl` switches it on
   uint32_t serial;        // 1: one warp, points in order (deterministic; testing)
+  unsigned long long* counters;  // optional {pops, distance evaluations (two distances each), points} (diagnostics)
   TensorMapStorage tmap;
 };
 
@@ -735,7 +753,7 @@ __device__ __forceinline__ void sym_stage_and_dist(WarpSmem& ws, const SymVec<FA
 }
 
 template <int NS, bool FAST, int D32, int NW>
-__global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ SymArgs a)
+__global__ void __launch_bounds__(CW * 32, FAST ? G200_SYM_MB : 1) sym_kernel(const __grid_constant__ SymArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
@@ -757,7 +775,9 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ Sy
   const float mean_nn1 = a.nn1_stats[0];
   const float xi = (a.measure == 0) ? __fmul_rn(__fmul_rn(__fmul_rn(mean_nn1, mean_nn1), a.tau_build), a.tau_build)
                                     : __fmul_rn(mean_nn1, a.tau_build);
+  unsigned long long tot_pops = 0, tot_dists = 0, tot_points = 0;
   for (; n < a.N_layer; n += a.serial ? 1u : a.N_layer) {
+  ++tot_points;
   if (a.serial) {
     __threadfence();  // the previous point's sym_buffer / sym_atomic writes (lane 0) are visible to every lane's loads
     __syncwarp();
@@ -861,6 +881,7 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ Sy
       const int anchor = L.pop(crit);
       if (anchor == EMPTY_KEY) break;
       V.insert(anchor);
+      ++tot_pops;
       for (uint32_t i = 0; i < K; i += 32) {
         const uint32_t kk = i + lane;
         int ck = EMPTY_KEY;
@@ -880,6 +901,7 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ Sy
         const unsigned mask = __ballot_sync(FULL, valid);
         const int cnt = __popc(mask);
         if (!cnt) continue;
+        tot_dists += cnt;
         __syncwarp();
         if (valid) ws.s_sorted[__popc(mask & ((1u << lane) - 1u))] = ck;
         __syncwarp();
@@ -926,6 +948,11 @@ __global__ void __launch_bounds__(CW * 32) sym_kernel(const __grid_constant__ Sy
     }
   }
   }  // points of this warp (one, unless serial)
+  if (a.counters && lane == 0) {
+    atomicAdd(&a.counters[0], tot_pops);
+    atomicAdd(&a.counters[1], tot_dists + tot_points * (K - K / 2));  // + the start point of every local link's search
+    atomicAdd(&a.counters[2], tot_points);
+  }
 }
 
 // ================================================================================================
@@ -1003,6 +1030,81 @@ static int launch_warp_kernel(Kern kern, const Args& a, uint32_t n_items, size_t
 }  // namespace g200
 
 using namespace g200;
+
+// ---- diagnostics: per-launch traversal counters + times of the construction kernels (thread-local recorder) ----
+namespace {
+struct BuildRecorder {
+  static constexpr uint32_t MAX = GGNN_B200_MAX_BUILD_PASSES;
+  unsigned long long* d_counters{nullptr};  // [MAX][4]
+  cudaEvent_t ev[MAX][2];
+  ggnn_b200_build_pass_stats meta[MAX];
+  uint32_t n{0};
+};
+thread_local BuildRecorder* g_rec = nullptr;
+
+// -> device counters of the next recorded pass (nullptr when not recording); the caller launches between begin / end
+unsigned long long* rec_begin(uint32_t kernel, uint32_t layer_top, uint32_t layer_btm, uint32_t points, cudaStream_t stream)
+{
+  BuildRecorder* r = g_rec;
+  if (!r || r->n >= BuildRecorder::MAX) return nullptr;
+  ggnn_b200_build_pass_stats& m = r->meta[r->n];
+  m = ggnn_b200_build_pass_stats{};
+  m.kernel = kernel;
+  m.layer_top = layer_top;
+  m.layer_btm = layer_btm;
+  m.points = points;
+  cudaEventRecord(r->ev[r->n][0], stream);
+  return r->d_counters + 4 * static_cast<size_t>(r->n);
+}
+void rec_end(unsigned long long* slot, cudaStream_t stream)
+{
+  if (!slot) return;
+  BuildRecorder* r = g_rec;
+  cudaEventRecord(r->ev[r->n][1], stream);
+  ++r->n;
+}
+}  // namespace
+
+extern "C" int ggnn_b200_build_stats_begin(void)
+{
+  if (g_rec) return set_error(GGNN_B200_ERR_INVALID, "build statistics are already being recorded on this thread");
+  BuildRecorder* r = new BuildRecorder();
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&r->d_counters), BuildRecorder::MAX * 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(r->d_counters, 0, BuildRecorder::MAX * 4 * sizeof(unsigned long long));
+  for (uint32_t i = 0; i < BuildRecorder::MAX && e == cudaSuccess; ++i)
+    for (int j = 0; j < 2 && e == cudaSuccess; ++j) e = cudaEventCreate(&r->ev[i][j]);
+  if (e != cudaSuccess) {
+    delete r;
+    return set_cuda_error(e, "build statistics set-up");
+  }
+  g_rec = r;
+  return 0;
+}
+
+extern "C" int ggnn_b200_build_stats_end(ggnn_b200_build_pass_stats* out, uint32_t max_passes, uint32_t* n_passes)
+{
+  BuildRecorder* r = g_rec;
+  if (!r) return set_error(GGNN_B200_ERR_INVALID, "build statistics are not being recorded on this thread");
+  g_rec = nullptr;
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned long long h[BuildRecorder::MAX * 4];
+  if (e == cudaSuccess) e = cudaMemcpy(h, r->d_counters, sizeof(h), cudaMemcpyDeviceToHost);
+  const uint32_t n = std::min(r->n, max_passes);
+  for (uint32_t i = 0; i < n && e == cudaSuccess && out; ++i) {
+    out[i] = r->meta[i];
+    out[i].pops = h[4 * i];
+    out[i].dists = h[4 * i + 1];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r->ev[i][0], r->ev[i][1]);
+    out[i].ms = ms;
+  }
+  if (n_passes) *n_passes = n;
+  for (uint32_t i = 0; i < BuildRecorder::MAX; ++i)
+    for (int j = 0; j < 2; ++j) cudaEventDestroy(r->ev[i][j]);
+  cudaFree(r->d_counters);
+  delete r;
+  return set_cuda_error(e, "build statistics read-back");
+}
 
 static int check_cfg(const ggnn_b200_graph_config* cfg)
 {
@@ -1147,6 +1249,7 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
   const bool g4 = f.fast && (f.d32 == 3 || f.d32 == 4) && env_u32("GGNN_B200_BUILD_STAGE_MODE", 3) == 3;
   if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, 16, g4 ? 16 : 0)) return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
+  a.counters = rec_begin(0, layer_top, layer_btm, a.N_btm, stream);
   int rc = -1;
 #define G200_MERGE(NS_, FAST_, D32_, NW_) \
   rc = launch_warp_kernel(merge_kernel<NS_, FAST_, D32_, NW_>, a, a.N_btm, smem, stream, "merge_kernel", true)
@@ -1174,6 +1277,7 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
     }
   }
 #undef G200_MERGE
+  rec_end(a.counters, stream);
   if (rc) return rc;
   // publish: graph_construction.cu:290-295
   cudaError_t e = cudaMemcpyAsync(g.graph + static_cast<size_t>(cfg->Ns_offsets[layer_btm]) * cfg->KBuild, d_graph_buffer,
@@ -1225,22 +1329,28 @@ extern "C" int ggnn_b200_sym(const ggnn_b200_graph_config* cfg, const float* d_b
   }
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
   a.serial = env_u32("GGNN_B200_SYM_SERIAL", 0) ? 1u : 0u;
+  a.counters = rec_begin(1, layer, layer, a.N_layer, stream);
+  int rc = -1;
 #define G200_SYM(NS_, FAST_, D32_, NW_) \
-  return launch_warp_kernel(sym_kernel<NS_, FAST_, D32_, NW_>, a, a.serial ? 1u : a.N_layer, smem, stream, "sym_kernel")
+  rc = launch_warp_kernel(sym_kernel<NS_, FAST_, D32_, NW_>, a, a.serial ? 1u : a.N_layer, smem, stream, "sym_kernel")
   if (f.fast) {
     switch (f.d32) {
-      case 1: G200_SYM(2, true, 1, 2);
-      case 2: G200_SYM(2, true, 2, 2);
-      case 3: G200_SYM(2, true, 3, 2);
-      case 4: G200_SYM(2, true, 4, 2);
+      case 1: G200_SYM(2, true, 1, 2); break;
+      case 2: G200_SYM(2, true, 2, 2); break;
+      case 3: G200_SYM(2, true, 3, 2); break;
+      case 4: G200_SYM(2, true, 4, 2); break;
     }
   }
-  switch (NS) {
-    case 2: G200_SYM(2, false, 1, 1);
-    case 3: G200_SYM(3, false, 1, 1);
+  else {
+    switch (NS) {
+      case 2: G200_SYM(2, false, 1, 1); break;
+      case 3: G200_SYM(3, false, 1, 1); break;
+      default: rc = set_error(GGNN_B200_ERR_UNSUPPORTED, "no sym kernel variant");
+    }
   }
 #undef G200_SYM
-  return set_error(GGNN_B200_ERR_UNSUPPORTED, "no sym kernel variant");
+  rec_end(a.counters, stream);
+  return rc;
 }
 
 extern "C" int ggnn_b200_sym_buffer_merge(const ggnn_b200_graph_config* cfg, uint32_t layer, const int32_t* d_sym_buffer,

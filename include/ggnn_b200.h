@@ -189,6 +189,20 @@ int ggnn_b200_build_graph(const ggnn_b200_graph_config* cfg, const float* d_base
 int ggnn_b200_refine_graph(const ggnn_b200_graph_config* cfg, const float* d_base, int32_t measure, float tau_build,
                            void* d_graph_blob, void* d_scratch, size_t scratch_bytes, ggnn_b200_stream_t stream);
 
+/* Diagnostics (roofline accounting of the construction kernels): between _begin and _end every
+ * ggnn_b200_merge / ggnn_b200_sym launch of the calling thread records its traversal counters and its time on the stream.
+ * Algorithmic bytes of a pass = 4*D*(points + dists) + 4*KBuild*pops (merge; sym evaluates two distances per row read).
+ * _begin allocates a small device buffer, _end synchronises the device and frees it. */
+#define GGNN_B200_MAX_BUILD_PASSES 64
+typedef struct {
+  uint32_t kernel;    /* 0 = merge, 1 = sym */
+  uint32_t layer_top, layer_btm, points;
+  uint64_t pops, dists;
+  float ms;
+} ggnn_b200_build_pass_stats;
+int ggnn_b200_build_stats_begin(void);
+int ggnn_b200_build_stats_end(ggnn_b200_build_pass_stats* out, uint32_t max_passes, uint32_t* n_passes);
+
 /* The reference keeps ONE cuRAND generator (XORWOW, seed 1234) per GPU whose sequence continues over all shards built on
  * that GPU (graph_construction.cu:96-102,127).  A caller that wants the reference's selection for every shard owns such a
  * generator and draws the uniforms of a build itself: ggnn_b200_rng_fill_build() makes the reference's three
