@@ -626,7 +626,7 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
                     "what": f"{a.n_base}x{a.dim} k_build={a.k_build} tau_build={a.tau_build} refine={a.refine}",
                     "layer0_passes": build_passes}}
 
-    def timed(fn, reps=3):
+    def timed(fn, reps=5):
         fn()
         torch.cuda.synchronize()
         ev = _events(2 * reps)
@@ -635,7 +635,7 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
             out = fn()
             ev[2 * r + 1].record()
         torch.cuda.synchronize()
-        return out, float(np.mean([ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps)]))
+        return out, float(np.median([ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps)]))
     # config 1: the README example -- 10 000 x 128 uniform base and 10 000 queries as CPU-resident tensors, everything
     # (host -> device copies, results back to the host) inside the timed call
     try:
@@ -663,7 +663,7 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
     # config 5: bf_query 1M x 10k as a tensor-core contraction (+ exact re-rank), k = 10 and the API default k = 100
     try:
         (bi, bd), ms10 = timed(lambda: idx.bf_query(query, K))
-        (bi100, _), ms100 = timed(lambda: idx.bf_query(query, 100), reps=2)
+        (bi100, _), ms100 = timed(lambda: idx.bf_query(query, 100), reps=3)
         flops = 2.0 * Nq * a.n_base * a.dim
         ex["bf_query"] = {"workload": f"{a.n_base}x{a.dim} base, {Nq} queries (BASELINE config 5)",
                           "k10_ms": ms10, "k100_ms": ms100, "k10_useful_tflops": flops / (ms10 * 1e-3) / 1e12,
@@ -716,7 +716,7 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
         h.set_base(hb)
         h.build(a.k_build, a.tau_build, a.refine)
         hgt, _ = h.bf_query(hq, K)
-        (hi, _), hms = timed(lambda: h.query(hq, K, a.hard_tau, a.hard_iterations))
+        (hi, _), hms = timed(lambda: h.query(hq, K, a.hard_tau, a.hard_iterations), reps=7)
         ex["hard_operating_point"] = {"workload": f"{a.n_base}x{a.dim} ({a.hard_kind}), {Nq} queries, tau_query={a.hard_tau} "
                                                   f"max_iterations={a.hard_iterations}", "single_batch_ms": hms,
                                       "queries_per_s": Nq / (hms * 1e-3), "recall_at_10": recall_at_k(hgt, hi, K),
@@ -742,8 +742,8 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
         g3.build(a.k_build, a.tau_build, a.refine, ggnn.DistanceMeasure.Cosine)
         torch.cuda.synchronize()
         b3_s = time.time() - t0
-        (gt3, _), bf3_ms = timed(lambda: g3.bf_query(q3, K, ggnn.DistanceMeasure.Cosine), reps=1)
-        (i3, _), q3_ms = timed(lambda: g3.query(q3, K, a.tau_query, a.max_iterations, ggnn.DistanceMeasure.Cosine))
+        (gt3, _), bf3_ms = timed(lambda: g3.bf_query(q3, K, ggnn.DistanceMeasure.Cosine), reps=2)
+        (i3, _), q3_ms = timed(lambda: g3.query(q3, K, a.tau_query, a.max_iterations, ggnn.DistanceMeasure.Cosine), reps=9)
         n_iter, n_dist, alg = _query_stats(g3, q3, K, a.tau_query, a.max_iterations, 1)
         peak, _ = measured_peaks()
         ex["config3"] = {"workload": f"{N3}x{D3} fp32 (manifoldcos8), cosine, {Nq} queries, k_query={K} tau_query={a.tau_query} "
