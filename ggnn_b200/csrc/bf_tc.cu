@@ -224,7 +224,7 @@ constexpr int TC_STAGES_TMEM = 6;
 constexpr uint32_t TC_CHUNK = 8;
 
 // KB k-blocks (D = 32*KB); KP = capacity of the per-row best lists (K <= KP); NSTAGE = depth of the B ring (the lists
-// and the ring share the shared memory: KP 32 -> 6 stages, KP 128 (the API's default KGT = 100) -> 2 stages)
+// and the ring share the shared memory: KP 32 -> 6 stages, KP 128 (the API default KGT = 100) -> 3 stages)
 template <int KB, int KP, int NSTAGE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs a)
 {
@@ -827,10 +827,10 @@ int tc_bf_query(const ggnn_b200_bf_query_params& p, uint32_t Nq, void* workspace
   if (workspace_bytes < w.total) return set_error(GGNN_B200_ERR_INVALID, "bf_query workspace too small");
   const bool small_k = p.KQuery <= 32;
   switch (p.D / 32) {
-    case 1: return small_k ? tc_run<1, 32, 6>(p, Nq, w, stream) : tc_run<1, 128, 2>(p, Nq, w, stream);
-    case 2: return small_k ? tc_run<2, 32, 6>(p, Nq, w, stream) : tc_run<2, 128, 2>(p, Nq, w, stream);
-    case 3: return small_k ? tc_run<3, 32, 6>(p, Nq, w, stream) : tc_run<3, 128, 2>(p, Nq, w, stream);
-    case 4: return small_k ? tc_run<4, 32, 6>(p, Nq, w, stream) : tc_run<4, 128, 2>(p, Nq, w, stream);
+    case 1: return small_k ? tc_run<1, 32, 6>(p, Nq, w, stream) : tc_run<1, 128, 3>(p, Nq, w, stream);
+    case 2: return small_k ? tc_run<2, 32, 6>(p, Nq, w, stream) : tc_run<2, 128, 3>(p, Nq, w, stream);
+    case 3: return small_k ? tc_run<3, 32, 6>(p, Nq, w, stream) : tc_run<3, 128, 3>(p, Nq, w, stream);
+    case 4: return small_k ? tc_run<4, 32, 6>(p, Nq, w, stream) : tc_run<4, 128, 3>(p, Nq, w, stream);
   }
   return set_error(GGNN_B200_ERR_UNSUPPORTED, "tensor-core bf_query needs D in {32, 64, 96, 128}");
 }

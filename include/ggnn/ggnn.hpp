@@ -7,8 +7,9 @@
 //
 // Same names, argument meaning, defaults and error behaviour (std::runtime_error / std::out_of_range for API
 // misuse).  All computation happens in the sm_100a kernels behind the C ABI; there is no CPU fallback.
-// Differences: uint8 vectors are widened to fp32 once on the device (bit-identical results, see
-// ggnn_b200_widen_u8); multi-GPU results are merged on the first GPU by a kernel -- the traversal kernels store their
+// Differences: uint8 vectors stay uint8 on the device and are read natively by the traversal kernel where it
+// has a variant (D % 32 == 0, D <= 256, KQuery <= 47); the other kernels run on rows widened on the device for the duration
+// of the call (bit-identical results, see ggnn_b200_widen_u8); multi-GPU results are merged on the first GPU by a kernel -- the traversal kernels store their
 // lists straight into its memory (peer access) -- instead of the reference's CPU heap merge, so results may stay on the
 // GPU for any number of GPUs; queryAsync() keeps several host batches in flight.  Shards that do not fit on their GPU
 // are swapped GPU <-> pinned host memory <-> part_<id>.ggnn files like the reference does (setCPUMemoryLimit /
@@ -686,9 +687,10 @@ class GGNN {
         // one cuRAND generator per GPU, continuing over its shards like the reference's (graph_construction.cu:96-102,127)
         if (!g.rng) detail::abi_check(ggnn_b200_rng_create(&g.rng, 1234ULL));
         detail::abi_check(ggnn_b200_rng_fill_build(g.rng, &s.cfg, d_rng, g.stream));
-        rc = ggnn_b200_build_graph(&s.cfg, slot.base.data(), static_cast<int>(measure), tau_build, refinement_iterations,
+        rc = ggnn_b200_build_graph(&s.cfg, rows_f32(g, slot), static_cast<int>(measure), tau_build, refinement_iterations,
                                    d_rng, slot.blob.data(), scratch, scratch_bytes, g.stream);
         cudaStreamSynchronize(g.stream);
+        drop_f32(g, slot);
         sh.has_graph = rc == 0;
         sh.dirty = true;
       }
@@ -774,13 +776,13 @@ class GGNN {
     }
     std::vector<Dataset<KeyT>> ids(n_gpus);
     std::vector<Dataset<ValueT>> dists(n_gpus);
-    std::vector<Dataset<float>> q_dev(n_gpus);
+    std::vector<Dataset<float>> q_dev(n_gpus);      // fp32 copy of the query batch on each GPU (made when a kernel needs it)
+    std::vector<Dataset<uint8_t>> q_u8(n_gpus);     // uint8 copy, for shards searched from native 1-byte rows
     std::vector<cudaEvent_t> evs(n_gpus, nullptr);
     // launch everything asynchronously on every GPU first
     for (uint32_t gi = 0; gi < n_gpus; ++gi) {
       Gpu& g = s.gpus[gi];
       detail::DeviceGuard guard(g.id);
-      q_dev[gi] = float_on_gpu(query, g.id, g.stream);
       if (!gather) {
         ids[gi] = Dataset<KeyT>::emptyOnGPU(Nq, KQuery * s.spg, g.id);
         dists[gi] = Dataset<ValueT>::emptyOnGPU(Nq, KQuery * s.spg, g.id);
@@ -796,7 +798,20 @@ class GGNN {
         const uint32_t sidx = reverse ? s.spg - 1 - i : i;
         Shard& sh = s.shards[g.first_shard + sidx];
         Slot& slot = acquire(g, sh);
+        const bool native = native_u8(slot, query, KQuery);
+        if (native) {
+          if (!q_u8[gi].data()) q_u8[gi] = u8_on_gpu(query, g.id, g.stream);
+        }
+        else {
+          if (!q_dev[gi].data()) q_dev[gi] = float_on_gpu(query, g.id, g.stream);
+          rows_f32(g, slot);
+        }
         ggnn_b200_query_params p = query_params(slot, q_dev[gi].data(), KQuery, tau_query, max_iterations, measure);
+        if (native) {
+          p.base_type = GGNN_B200_BASE_U8;
+          p.d_base = reinterpret_cast<const float*>(slot.base_u8.data());
+          p.d_query = reinterpret_cast<const float*>(q_u8[gi].data());
+        }
         if (gather) {
           p.n_scatter = 1;
           p.scatter_slot = gi * s.spg + sidx;
@@ -907,19 +922,34 @@ class GGNN {
     p.ids.reserve(r_words * sizeof(KeyT));
     p.dists.reserve(r_words * sizeof(ValueT));
     const float* dq = static_cast<const float*>(p.query.ptr);
+    bool widened = false;
     if (query.type == DataType::FLOAT) {
       detail::cuda_check(cudaMemcpyAsync(p.query.ptr, static_cast<const void*>(query), q_bytes, cudaMemcpyHostToDevice, p.stream), "cudaMemcpyAsync(query)");
     }
-    else {  // uint8: copy the bytes, widen on the device (exact)
+    else {  // uint8: copy the bytes; widened on the device (exact) only if a shard is not searched from native 1-byte rows
       p.stage.reserve(query.numel());
       detail::cuda_check(cudaMemcpyAsync(p.stage.ptr, static_cast<const void*>(query), query.numel(), cudaMemcpyHostToDevice, p.stream), "cudaMemcpyAsync(query)");
-      detail::abi_check(ggnn_b200_widen_u8(static_cast<const uint8_t*>(p.stage.ptr), static_cast<float*>(p.query.ptr), query.numel(), p.stream));
     }
     KeyT* d_ids = static_cast<KeyT*>(p.ids.ptr);
     ValueT* d_dists = static_cast<ValueT*>(p.dists.ptr);
     for (uint32_t i = 0; i < s.spg; ++i) {
       Shard& sh = s.shards[g.first_shard + i];
-      ggnn_b200_query_params qp = query_params(g.slots[sh.slot], dq, KQuery, tau_query, max_iterations, measure);
+      Slot& slot = g.slots[sh.slot];
+      const bool native = native_u8(slot, query, KQuery);
+      if (!native && query.type != DataType::FLOAT && !widened) {
+        detail::abi_check(ggnn_b200_widen_u8(static_cast<const uint8_t*>(p.stage.ptr), static_cast<float*>(p.query.ptr), query.numel(), p.stream));
+        widened = true;
+      }
+      if (!native && !slot.base.data()) {  // widened rows are made on the GPU's own stream: order this pipeline behind it
+        rows_f32(g, slot);
+        detail::cuda_check(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");
+      }
+      ggnn_b200_query_params qp = query_params(slot, dq, KQuery, tau_query, max_iterations, measure);
+      if (native) {
+        qp.base_type = GGNN_B200_BASE_U8;
+        qp.d_base = reinterpret_cast<const float*>(slot.base_u8.data());
+        qp.d_query = static_cast<const float*>(p.stage.ptr);
+      }
       qp.d_query_results = d_ids;
       qp.d_query_results_dists = d_dists;
       qp.shards_per_gpu = s.spg;
@@ -955,7 +985,11 @@ class GGNN {
     detail::DeviceGuard g(gpu);
     Dataset<float> b_dev;
     const float* db = nullptr;
-    if (s.shards.size() == 1 && s.shards[0].slot >= 0) db = s.gpus[0].slots[s.shards[0].slot].base.data();
+    Slot* single = (s.shards.size() == 1 && s.shards[0].slot >= 0) ? &s.gpus[0].slots[s.shards[0].slot] : nullptr;
+    if (single) {
+      db = rows_f32(s.gpus[0], *single);
+      detail::cuda_check(cudaStreamSynchronize(s.gpus[0].stream), "cudaStreamSynchronize");
+    }
     else {
       b_dev = float_on_gpu(*s.base, gpu, nullptr);
       db = b_dev.data();
@@ -972,6 +1006,7 @@ class GGNN {
     const int rc = ggnn_b200_bf_query(&p, static_cast<uint32_t>(query.N), nullptr);
     cudaDeviceSynchronize();
     if (p.d_workspace) cudaFree(p.d_workspace);
+    if (single) drop_f32(s.gpus[0], *single);
     detail::abi_check(rc);
     return s.return_results_on_gpu ? std::move(out) : to_host(std::move(out));
   }
@@ -1020,7 +1055,8 @@ class GGNN {
   };
   /// one (base rows, graph blob) buffer pair on a GPU
   struct Slot {
-    Dataset<float> base;
+    Dataset<float> base;        // fp32 rows (for a uint8 base: widened on demand, see rows_f32 / drop_f32)
+    Dataset<uint8_t> base_u8;   // native 1-byte rows of a uint8 base (resident mode)
     Dataset<uint8_t> blob;
     int64_t resident{-1};  // global shard id held, -1 = free
     uint64_t last_use{0};
@@ -1110,12 +1146,38 @@ class GGNN {
     p.D = s.cfg.D; p.measure = static_cast<int>(measure); p.KQuery = KQuery;
     p.tau_query = tau_query; p.max_iterations = max_iterations;
     p.N_base = static_cast<int32_t>(s.cfg.N); p.KBuild = s.cfg.KBuild; p.num_starting_points = s.cfg.S;
-    p.d_base = slot.base.data(); p.d_query = dq;
+    p.d_base = slot.base.data(); p.d_query = dq;  // (callers override both for native uint8 rows)
     p.d_graph = reinterpret_cast<const KeyT*>(blob + s.off.graph);
     p.d_starting_points = reinterpret_cast<const KeyT*>(blob + s.off.translation) + s.cfg.STs_offsets[GGNN_B200_L - 1];
     p.d_nn1_stats = reinterpret_cast<const ValueT*>(blob + s.off.nn1_stats);
     p.shards_per_gpu = 1;
     return p;
+  }
+
+  /// fp32 rows of a slot; the rows of a natively stored uint8 base are widened on the device on demand (exact: the
+  /// reference computes on static_cast<float>(value), distance.cuh:104-148)
+  const float* rows_f32(Gpu& g, Slot& slot)
+  {
+    if (!slot.base.data() && slot.base_u8.data()) {
+      slot.base = Dataset<float>::emptyOnGPU(slot.base_u8.N, slot.base_u8.D, g.id);
+      detail::abi_check(ggnn_b200_widen_u8(slot.base_u8.data(), slot.base.data(), slot.base_u8.numel(), g.stream));
+    }
+    return slot.base.data();
+  }
+  /// release the widened copy of a natively stored uint8 shard again (GGNN_B200_KEEP_WIDENED=1 keeps it)
+  void drop_f32(Gpu& g, Slot& slot)
+  {
+    if (slot.base_u8.data() && slot.base.data() && !std::getenv("GGNN_B200_KEEP_WIDENED")) {
+      cudaStreamSynchronize(g.stream);
+      slot.base = Dataset<float>{};
+    }
+  }
+  /// does the traversal kernel read this slot's 1-byte rows natively for this query?  (include/ggnn_b200.h: D % 32 == 0,
+  /// D <= 256, KQuery <= 47)
+  bool native_u8(const Slot& slot, const GenericDataset& query, uint32_t KQuery) const
+  {
+    return slot.base_u8.data() && query.type == DataType::UINT8 && st->cfg.D % 32 == 0 && st->cfg.D <= 256 && KQuery <= 47 &&
+           !std::getenv("GGNN_B200_NO_NATIVE_U8");
   }
 
   /// the device buffers holding `sh` (current device = g.id).  Resident mode: its own slot.  Swap mode
@@ -1200,6 +1262,16 @@ class GGNN {
     if (q.D != st->base->D) throw std::out_of_range("query dimension does not match the base");
   }
 
+  /// a uint8 dataset as it is on `gpu` (referenced when already there)
+  static Dataset<uint8_t> u8_on_gpu(const GenericDataset& src, int gpu, cudaStream_t stream)
+  {
+    GenericDataset rows = src.reference();
+    if (rows.isGPUAccessible() && (rows.gpu_id == gpu || rows.location == DataLocation::MANAGED)) return Dataset<uint8_t>{std::move(rows)};
+    Dataset<uint8_t> d = Dataset<uint8_t>::emptyOnGPU(src.N, src.D, gpu);
+    detail::cuda_check(cudaMemcpyAsync(d.data(), static_cast<const void*>(rows), rows.required_size_bytes(), cudaMemcpyDefault, stream), "cudaMemcpyAsync(uint8 query)");
+    return d;
+  }
+
   /// rows [from, from + num) of `src` (float or uint8, anywhere) as fp32 on `gpu`; uint8 is widened on the device.
   /// Already-resident float data is referenced, not copied -- unless `into` names the buffer to fill (swap slots).
   /// The current device must be `gpu`.
@@ -1251,7 +1323,7 @@ class GGNN {
     detail::abi_check(ggnn_b200_graph_config_init(&s.cfg, static_cast<uint32_t>(n_shard), s.base->D, KBuild));
     ggnn_b200_graph_blob_offsets(&s.cfg, &s.off);
     s.blob_bytes = s.off.total;
-    const size_t shard_bytes = n_shard * s.base->D * sizeof(float) + s.blob_bytes;
+    const size_t shard_bytes = n_shard * s.base->D * sizeof(float) + s.blob_bytes;  // (uint8 bases: upper bound)
     const size_t scratch_bytes = ggnn_b200_build_scratch_bytes(&s.cfg);
     s.shards.resize(num_shards);
     s.gpus.resize(s.gpu_ids.size());
@@ -1264,8 +1336,7 @@ class GGNN {
       detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&g.work_counter), 16), "cudaMalloc");
       detail::cuda_check(cudaMalloc(reinterpret_cast<void**>(&g.d_gather_tbl), 16), "cudaMalloc");
       // a base that already lives on this GPU stays there (referenced, never swapped)
-      const bool base_on_gpu = s.base->isGPUAccessible() && s.base->type == DataType::FLOAT &&
-                               (s.base->gpu_id == g.id || s.base->location == DataLocation::MANAGED);
+      const bool base_on_gpu = s.base->isGPUAccessible() && (s.base->gpu_id == g.id || s.base->location == DataLocation::MANAGED);
       uint32_t n_buf = s.spg;
       if (!base_on_gpu) {
         size_t free_b = 0, total_b = 0;
@@ -1288,7 +1359,17 @@ class GGNN {
         sh.global_id = g.first_shard + i;
         if (!g.swap) {  // resident: shard i <-> slot i for good
           Slot& slot = g.slots[i];
-          slot.base = float_on_gpu(*s.base, g.id, g.stream, static_cast<uint64_t>(sh.global_id) * n_shard, n_shard);
+          if (s.base->type == DataType::UINT8) {  // 1-byte rows stay 1-byte rows on the device
+            GenericDataset rows = s.base->referenceRange(static_cast<uint64_t>(sh.global_id) * n_shard, n_shard);
+            const bool on_gpu = rows.isGPUAccessible() && (rows.gpu_id == g.id || rows.location == DataLocation::MANAGED);
+            if (on_gpu) slot.base_u8 = Dataset<uint8_t>{std::move(rows)};
+            else {
+              slot.base_u8 = Dataset<uint8_t>::emptyOnGPU(n_shard, s.base->D, g.id);
+              detail::cuda_check(cudaMemcpyAsync(slot.base_u8.data(), static_cast<const void*>(rows), rows.required_size_bytes(),
+                                                 cudaMemcpyDefault, g.stream), "cudaMemcpyAsync(uint8 rows)");
+            }
+          }
+          else slot.base = float_on_gpu(*s.base, g.id, g.stream, static_cast<uint64_t>(sh.global_id) * n_shard, n_shard);
           slot.resident = sh.global_id;
           sh.slot = static_cast<int>(i);
         }

@@ -116,6 +116,36 @@ int main(int argc, char** argv)
       unsetenv("GGNN_B200_NO_PEER_GATHER");
     }
   }
+  {  // uint8 base: 1-byte rows read natively by the traversal kernel == the widened fp32 path (same stored graph)
+    const uint32_t D8 = 64;
+    const size_t N8 = 20000, Nq8 = 2000;
+    std::vector<uint8_t> b8(N8 * D8), q8(Nq8 * D8);
+    for (auto& x : b8) x = static_cast<uint8_t>(prng() & 0xff);
+    for (auto& x : q8) x = static_cast<uint8_t>(prng() & 0xff);
+    Dataset<uint8_t> base8 = Dataset<uint8_t>::copy(b8, D8, true);
+    Dataset<uint8_t> query8 = Dataset<uint8_t>::copy(q8, D8, true);
+    const std::string dir8 = dir + "/u8";
+    GGNN<int32_t, float> n{};
+    n.setWorkingDirectory(dir8);
+    n.setBaseReference(base8);
+    n.build(24, 0.5f);
+    n.store();
+    const auto r_native = n.query(query8, K, 0.64f, 400);
+    auto h_native = n.queryAsync(query8, K, 0.64f, 400);
+    const bool async_ok = same(h_native.get(), r_native);
+    const auto gt8 = n.bfQuery(query8, K);
+    setenv("GGNN_B200_NO_NATIVE_U8", "1", 1);
+    GGNN<int32_t, float> w{};
+    w.setWorkingDirectory(dir8);
+    w.setBaseReference(base8);
+    w.load(24);
+    const auto r_widened = w.query(query8, K, 0.64f, 400);
+    unsetenv("GGNN_B200_NO_NATIVE_U8");
+    check(same(r_native, r_widened) && async_ok, "uint8 base: native rows == widened rows (query, queryAsync)");
+    size_t hits = 0;
+    for (size_t i = 0; i < Nq8; ++i) hits += r_native.ids[i * K] == gt8.ids[i * K];
+    check(hits > Nq8 / 2 && r_native.dists[0] == static_cast<float>(static_cast<int>(r_native.dists[0])), "uint8 base: integer distances, top-1 mostly exact");
+  }
   std::printf("%s\n", failures ? "FAILED" : "ALL OK");
   return failures ? 1 : 0;
 }
