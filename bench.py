@@ -729,32 +729,26 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
         ex["cpp_host"] = cpp_host_bench(a, idx, base, query)
     except Exception as e:  # noqa: BLE001
         ex["cpp_host"] = {"error": repr(e)[-300:]}
-    # config 3: 10M x 96 cosine, build + query on one GPU
+    # config 3: 10M x 96 cosine, build + query on one GPU -- in a process of its own (tools/shard_probe.py), so that the
+    # figure does not depend on what this process has allocated and freed before
     try:
         torch.cuda.empty_cache()
-        N3, D3 = a.c3_n, 96
-        b3, q3 = gen_gpu(N3, Nq, D3, "manifoldcos8", a.seed, dev)
-        g3 = ggnn.GGNN()
-        g3.set_return_results_on_gpu(True)
-        g3.set_base(b3)
-        torch.cuda.synchronize()
-        t0 = time.time()
-        g3.build(a.k_build, a.tau_build, a.refine, ggnn.DistanceMeasure.Cosine)
-        torch.cuda.synchronize()
-        b3_s = time.time() - t0
-        (gt3, _), bf3_ms = timed(lambda: g3.bf_query(q3, K, ggnn.DistanceMeasure.Cosine), reps=2)
-        (i3, _), q3_ms = timed(lambda: g3.query(q3, K, a.tau_query, a.max_iterations, ggnn.DistanceMeasure.Cosine), reps=9)
-        n_iter, n_dist, alg = _query_stats(g3, q3, K, a.tau_query, a.max_iterations, 1)
+        env = dict(os.environ, PROBE_BF="1")
+        p3 = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shard_probe.py"), str(a.c3_n), "96", "manifoldcos8", "1", "12",
+                             str(a.tau_query), str(a.max_iterations)], capture_output=True, text=True, timeout=900, env=env)
+        if p3.returncode != 0:
+            raise RuntimeError(p3.stderr[-300:])
+        r3 = json.loads([ln for ln in p3.stdout.splitlines() if ln.startswith("{")][-1])
         peak, _ = measured_peaks()
-        ex["config3"] = {"workload": f"{N3}x{D3} fp32 (manifoldcos8), cosine, {Nq} queries, k_query={K} tau_query={a.tau_query} "
-                                     f"max_iterations={a.max_iterations}", "build_s": b3_s, "bf_query_ms": bf3_ms,
-                         "single_batch_ms": q3_ms, "queries_per_s": Nq / (q3_ms * 1e-3), "recall_at_10": recall_at_k(gt3, i3, K),
-                         "pops_per_query": n_iter / Nq, "dists_per_query": n_dist / Nq,
-                         "roofline": {"bound": "hbm", "achieved": alg / (q3_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                      "frac": alg / (q3_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg},
-                         "bf_ids_crc32": _crc(gt3)}
-        del g3, b3, q3
-        torch.cuda.empty_cache()
+        ex["config3"] = {"workload": f"{a.c3_n}x96 fp32 (manifoldcos8), cosine, {Nq} queries, k_query={K} tau_query={a.tau_query} "
+                                     f"max_iterations={a.max_iterations} (own process: tools/shard_probe.py)",
+                         "build_s": r3["build_s"], "bf_query_ms": r3.get("bf_query_ms"), "single_batch_ms": r3["query_ms_median"],
+                         "queries_per_s": Nq / (r3["query_ms_median"] * 1e-3), "recall_at_10": r3.get("recall_at_10"),
+                         "pops_per_query": r3["pops_per_query"], "dists_per_query": r3["dists_per_query"],
+                         "roofline": {"bound": "hbm", "achieved": r3["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
+                                      "frac": r3["algorithmic_gbs"] / peak,
+                                      "algorithmic_bytes_per_launch": r3["algorithmic_bytes_per_launch"]},
+                         "bf_ids_crc32": r3.get("bf_ids_crc32")}
     except Exception as e:  # noqa: BLE001
         ex["config3"] = {"error": repr(e)[-300:]}
     return ex

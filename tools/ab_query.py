@@ -17,13 +17,28 @@ import ggnn_b200 as ggnn  # noqa: E402
 
 def main():
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+    D = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    kind = sys.argv[3] if len(sys.argv) > 3 else "manifold8"
+    measure = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     dev = torch.device("cuda", 0)
-    base, qs = bench.gen_gpu(N, 40_000, 128, "manifold8", 1234, dev)
+    base, qs = bench.gen_gpu(N, 40_000, D, kind, 1234, dev)
     batches = [qs[i * 10000:(i + 1) * 10000] for i in range(4)]
     idx = ggnn.GGNN()
     idx.set_return_results_on_gpu(True)
     idx.set_base(base)
-    idx.build(24, 0.5)
+    idx.build(24, 0.5, 2, measure)
+    if measure or kind != "manifold8":   # no uint8 twin: fp32 only
+        out = {"lib": os.environ.get("GGNN_B200_LIB", "default"), "N": N, "D": D, "kind": kind, "measure": measure}
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(80)]
+        idx.query(batches[0], 10, 0.64, 400, measure)
+        for i in range(40):
+            ev[2 * i].record()
+            idx.query(batches[i % 4], 10, 0.64, 400, measure)
+            ev[2 * i + 1].record()
+        torch.cuda.synchronize()
+        out["single_ms"] = float(np.median([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(40)]))
+        print(json.dumps(out), flush=True)
+        return
     g8 = ggnn.GGNN()
     g8.set_return_results_on_gpu(True)
     g8.set_base(base.to(torch.uint8))

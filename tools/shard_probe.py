@@ -48,6 +48,17 @@ def main():
     if os.environ.get("PROBE_RECALL"):
         gt, _ = idx.bf_query(query[:2000].contiguous(), K, measure)
         rep["recall_at_10_first_2000"] = bench.recall_at_k(gt, ids[:2000], K)
+    if os.environ.get("PROBE_BF"):  # exact ground truth for the whole batch: time, recall, checksum
+        idx.bf_query(query, K, measure)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gt, _ = idx.bf_query(query, K, measure)
+        e1.record()
+        torch.cuda.synchronize()
+        rep["bf_query_ms"] = e0.elapsed_time(e1)
+        rep["recall_at_10"] = bench.recall_at_k(gt, ids, K)
+        rep["bf_ids_crc32"] = bench._crc(gt)
     print(json.dumps(rep), flush=True)
 
 
