@@ -39,8 +39,11 @@ struct WarpPlan {
   uint32_t warp_smem_bytes, stage_rows, hsize, ring_cap, stage_mode;
   uint32_t off_sq, off_half, off_sorted, off_hash, off_ring, off_bar;
 };
+// overlay_sorted: the sorted-key mirror / compaction scratch of `fetch` lives in the first bytes of the stage buffer (it is
+// only used between the end of one fetch's distance phase and the next fetch's row copies) -- 256 bytes per warp that
+// decide between 5 and 6 resident CTAs per SM for the merge kernel
 static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uint32_t sorted, uint32_t cache,
-                     uint32_t max_pops, uint32_t target_warps_per_sm, uint32_t force_rows = 0)
+                     uint32_t max_pops, uint32_t target_warps_per_sm, uint32_t force_rows = 0, bool overlay_sorted = false)
 {
   const DeviceInfo& dev = device_info();
   const uint32_t row_bytes = D * 4;
@@ -48,7 +51,7 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   pl.ring_cap = (vcap && vcap < max_pops) ? vcap : 0;
   pl.hsize = cache ? std::max(64u, bit_ceil_u32(max_pops + max_pops / 4 + 1)) : 0;  // see query.cu
   const uint32_t fixed = (need_sq ? align_up(row_bytes, 16) : 0) + (need_half ? align_up(row_bytes, 16) : 0) +
-                         align_up(sorted * 4, 16) + pl.hsize * 4 + align_up(pl.ring_cap * 4, 16) + 32;
+                         (overlay_sorted ? 0 : align_up(sorted * 4, 16)) + pl.hsize * 4 + align_up(pl.ring_cap * 4, 16) + 32;
   const uint32_t budget = (dev.smem_per_sm - 1024 * (target_warps_per_sm / CW + 1)) / target_warps_per_sm;
   uint32_t rows = budget > fixed ? (budget - fixed) / row_bytes : 0;
   rows = std::max(8u, std::min(32u, rows / 8 * 8));
@@ -63,8 +66,8 @@ static int make_plan(WarpPlan& pl, uint32_t D, bool need_sq, bool need_half, uin
   off += need_sq ? align_up(row_bytes, 16) : 0;
   pl.off_half = off;
   off += need_half ? align_up(row_bytes, 16) : 0;
-  pl.off_sorted = off;
-  off += align_up(sorted * 4, 16);
+  pl.off_sorted = overlay_sorted ? 0 : off;
+  off += overlay_sorted ? 0 : align_up(sorted * 4, 16);
   pl.off_hash = off;
   off += pl.hsize * 4;
   pl.off_ring = off;
@@ -1247,7 +1250,9 @@ extern "C" int ggnn_b200_merge(const ggnn_b200_graph_config* cfg, const float* d
   f.fast = f.fast && f.nw == 1 && NS == 2;  // the register-resident variants that are instantiated
   // gather4 staging (two 8-row buffers) for the register-resident variants with 384/512-byte rows
   const bool g4 = f.fast && (f.d32 == 3 || f.d32 == 4) && env_u32("GGNN_B200_BUILD_STAGE_MODE", 3) == 3;
-  if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, 16, g4 ? 16 : 0)) return rc;
+  if (int rc = make_plan(a.pl, a.D, !f.fast, false, a.sorted, a.cache, a.max_iterations, g4 ? 4 * G200_MERGE_MB : 16, g4 ? 16 : 0,
+                         g4 && G200_MERGE_MB > 5))
+    return rc;
   const size_t smem = static_cast<size_t>(a.pl.warp_smem_bytes) * CW;
   a.counters = rec_begin(0, layer_top, layer_btm, a.N_btm, stream);
   int rc = -1;

