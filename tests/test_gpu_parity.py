@@ -1014,6 +1014,27 @@ def test_native_uint8_api_paths_agree(monkeypatch):
     assert torch.equal(i1, i2) and torch.equal(d1, d2)
     gt, _ = g.bf_query(q, 10)
     assert ggnn.Evaluator(None, None, gt, 10).evaluate_results(i1).c_k_query > 0.5
+    monkeypatch.delenv("GGNN_B200_NO_NATIVE_U8")
+    # uint8 base in swap mode (2 shards, 1 device buffer): the slots hold widened rows; same results as resident shards
+    monkeypatch.setenv("GGNN_B200_GPU_SHARD_BUFFERS", "0")
+    r = ggnn.GGNN()
+    r.set_shard_size(4000)
+    r.set_base(torch.from_numpy(base_u8))
+    r.build(24, 0.5)
+    import tempfile
+    with tempfile.TemporaryDirectory() as wd:
+        r.set_working_directory(wd)
+        r.store()
+        ri, rd = r.query(q, 10, 0.64, 400)
+        monkeypatch.setenv("GGNN_B200_GPU_SHARD_BUFFERS", "1")
+        s = ggnn.GGNN()
+        s.set_working_directory(wd)
+        s.set_shard_size(4000)
+        s.set_base(torch.from_numpy(base_u8))
+        s.load(24)
+        assert s._pools[0] is not None
+        si, sd = s.query(q, 10, 0.64, 400)
+    assert torch.equal(ri, si) and torch.equal(rd, sd)
 
 
 def test_gpu_resident_tensors_are_used_in_place():
