@@ -383,7 +383,7 @@ class GGNN:
                 p.N_base, p.KBuild, p.num_starting_points = cfg.N, cfg.KBuild, cfg.S
                 # uint8 base: native 1-byte rows where the kernel has a variant, else rows widened on the device
                 native = (sh.pool is None and sh.base_u8 is not None and q_dev.dtype == torch.uint8 and
-                          cfg.D % 32 == 0 and cfg.D <= 256 and int(k_query) <= 47 and
+                          cfg.D in (32, 64, 96, 128, 256) and int(k_query) <= 47 and
                           not os.environ.get("GGNN_B200_NO_NATIVE_U8"))
                 if native:
                     p.base_type = 1

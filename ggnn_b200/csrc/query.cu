@@ -196,11 +196,17 @@ static int launch(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream
 // below 2^24 for D <= 256, so the reference's fp32 accumulation of static_cast<float>(value) terms
 // (distance.cuh:104-148) yields the same numbers in any order.
 // ================================================================================================
-template <class LT, int W, bool FULLW, bool FILTER>
-__device__ __forceinline__ void fetch_u8(LT& L, const VisitedSet& V, WarpSmem& ws, const uint32_t (&q)[W], float q_norm, int measure,
-                                         uint32_t words, int ck, float xi, Stats& st, const int* __restrict__ pf_graph,
+// D32 = D / 32 is a compile-time constant: the row offsets are immediates of the LDS instructions.  Per row and lane:
+// LDS.32 + VABSDIFF4 + IDP4A + REDUX + (compare, select) -- the conversion to float and the cosine finish happen once per
+// lane after all rows.
+template <class LT, int D32, bool FILTER>
+__device__ __forceinline__ void fetch_u8(LT& L, const VisitedSet& V, WarpSmem& ws, const uint32_t (&q)[(D32 + 3) / 4], float q_norm,
+                                         int measure, int ck, float xi, Stats& st, const int* __restrict__ pf_graph,
                                          uint32_t pf_stride, SpecRow* spec)
 {
+  constexpr int WORDS = 8 * D32;        // 32-bit words per row
+  constexpr int W = (D32 + 3) / 4;      // words per lane
+  constexpr bool FULLW = (D32 % 4) == 0;
   const int lane = lane_id();
   bool valid = ck != EMPTY_KEY;
   if constexpr (FILTER) {
@@ -219,49 +225,69 @@ __device__ __forceinline__ void fetch_u8(LT& L, const VisitedSet& V, WarpSmem& w
   const int key_r = ws.s_sorted[lane];
 
   // all rows of the fetch in flight at once: lane 4j fetches candidates 4j .. 4j+3 with ONE instruction
-  const uint32_t row_bytes = words * 4u;
+  constexpr uint32_t ROW_BYTES = WORDS * 4u;
   const int mp = lane < cnt ? key_r : ws.pad_row;
   const int m1 = __shfl_down_sync(FULL, mp, 1);
   const int m2 = __shfl_down_sync(FULL, mp, 2);
   const int m3 = __shfl_down_sync(FULL, mp, 3);
   const uint32_t bar_s = smem_u32(ws.bar);
-  if (lane == 0) mbar_expect_tx_s(bar_s, static_cast<uint32_t>((cnt + 3) & ~3) * row_bytes);
+  if (lane == 0) mbar_expect_tx_s(bar_s, static_cast<uint32_t>((cnt + 3) & ~3) * ROW_BYTES);
   if ((lane & 3) == 0 && lane < cnt)
-    tma_gather4_s(smem_u32(ws.stage) + static_cast<uint32_t>(lane) * row_bytes, ws.tmap, mp, m1, m2, m3, bar_s);
+    tma_gather4_s(smem_u32(ws.stage) + static_cast<uint32_t>(lane) * ROW_BYTES, ws.tmap, mp, m1, m2, m3, bar_s);
   mbar_wait_s(bar_s, ws.parity & 1u);
   ws.parity ^= 1u;
 
-  const uint32_t* rows = reinterpret_cast<const uint32_t*>(ws.stage);
-  float mine = G200_INF;
-  for (int r0 = 0; r0 < cnt; r0 += 4) {  // (rows past cnt hold zero fill or stale bytes: their results are never used)
-    unsigned acc[4], nrm[4];
+  // lane t owns words t (and t + 32) of every row; lanes past the end of a short row contribute nothing
+  const bool in0 = FULLW || W > 1 || lane < WORDS;
+  const bool in1 = W > 1 && (FULLW || lane + 32 < WORDS);
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(ws.stage) + (in0 ? lane : 0);
+  const uint32_t q0 = in0 ? q[0] : 0u, q1 = (W > 1 && in1) ? q[W - 1] : 0u;
+  unsigned mine_a = 0u, mine_n = 0u;  // this lane's candidate: sum (b-q)^2 | dot, and |b|^2 (cosine)
+  if (measure == 0) {
+    for (int r0 = 0; r0 < cnt; r0 += 8) {  // (rows past cnt hold zero fill or stale bytes: their results are never used)
+      const int li = lane - r0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[i] = 0u;
-      nrm[i] = 0u;
-      const uint32_t* row = rows + static_cast<uint32_t>(r0 + i) * words;
-#pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const uint32_t idx = lane + 32u * w;
-        const uint32_t b = (FULLW || idx < words) ? row[idx] : 0u;
-        if (measure == 0) {
-          const uint32_t s = __vabsdiffu4(b, q[w]);
-          acc[i] = __dp4a(s, s, acc[i]);
+      for (int i = 0; i < 8; ++i) {
+        uint32_t b0 = rp[i * WORDS];
+        if (!in0) b0 = 0u;
+        const uint32_t s0 = __vabsdiffu4(b0, q0);
+        unsigned acc = __dp4a(s0, s0, 0u);
+        if constexpr (W > 1) {
+          uint32_t b1 = in1 ? rp[i * WORDS + 32] : 0u;
+          const uint32_t s1 = __vabsdiffu4(b1, q1);
+          acc = __dp4a(s1, s1, acc);
         }
-        else {
-          acc[i] = __dp4a(b, q[w], acc[i]);
-          nrm[i] = __dp4a(b, b, nrm[i]);
-        }
+        const unsigned tot = __reduce_add_sync(FULL, acc);
+        if (li == i) mine_a = tot;
       }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const unsigned tot = __reduce_add_sync(FULL, acc[i]);
-      float d = static_cast<float>(tot);
-      if (measure != 0) d = cosine_finish(d, static_cast<float>(__reduce_add_sync(FULL, nrm[i])), q_norm);
-      if (lane == r0 + i) mine = d;
+      rp += 8 * WORDS;
     }
   }
+  else {
+    for (int r0 = 0; r0 < cnt; r0 += 8) {
+      const int li = lane - r0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t b0 = rp[i * WORDS];
+        if (!in0) b0 = 0u;
+        unsigned dot = __dp4a(b0, q0, 0u), nrm = __dp4a(b0, b0, 0u);
+        if constexpr (W > 1) {
+          uint32_t b1 = in1 ? rp[i * WORDS + 32] : 0u;
+          dot = __dp4a(b1, q1, dot);
+          nrm = __dp4a(b1, b1, nrm);
+        }
+        const unsigned td = __reduce_add_sync(FULL, dot), tn = __reduce_add_sync(FULL, nrm);
+        if (li == i) {
+          mine_a = td;
+          mine_n = tn;
+        }
+      }
+      rp += 8 * WORDS;
+    }
+  }
+  float mine = G200_INF;
+  if (lane < cnt)
+    mine = measure == 0 ? static_cast<float>(mine_a) : cosine_finish(static_cast<float>(mine_a), static_cast<float>(mine_n), q_norm);
   __syncwarp();  // all reads of the stage are done before the next fetch overwrites it
   finish_fetch<LT, FILTER>(L, key_r, mine, cnt, xi, pf_graph, pf_stride, spec);
 }
@@ -269,9 +295,11 @@ __device__ __forceinline__ void fetch_u8(LT& L, const VisitedSet& V, WarpSmem& w
 #ifndef G200_QUERY_MB_U8
 #define G200_QUERY_MB_U8 8  // 32 warps per SM (64 registers): 0.344 vs 0.392 ms per batch with 24
 #endif
-template <class LT, int W, bool FULLW>
+template <class LT, int D32>
 __global__ void __launch_bounds__(128, G200_QUERY_MB_U8) query_kernel_u8(const __grid_constant__ QueryArgs a)
 {
+  constexpr int W = (D32 + 3) / 4;
+  constexpr bool FULLW = (D32 % 4) == 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
@@ -330,7 +358,7 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB_U8) query_kernel_u8(const _
 
     for (uint32_t i = 0; i < p.num_starting_points; i += 32) {  // query_layer.cu:55
       const int ck = (i + lane < p.num_starting_points) ? p.d_starting_points[i + lane] : EMPTY_KEY;
-      fetch_u8<LT, W, FULLW, false>(L, V, ws, q, q_norm, p.measure, words, ck, xi, st, a.prefetch ? p.d_graph : nullptr, p.KBuild, nullptr);
+      fetch_u8<LT, D32, false>(L, V, ws, q, q_norm, p.measure, ck, xi, st, a.prefetch ? p.d_graph : nullptr, p.KBuild, nullptr);
     }
     SpecRow spec{EMPTY_KEY, EMPTY_KEY};
     for (uint32_t ite = 0; ite < p.max_iterations; ++ite) {  // :58-76
@@ -347,8 +375,8 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB_U8) query_kernel_u8(const _
         if (use_spec && spec.key == anchor) ck = spec.row;
         else ck = (i + lane < p.KBuild) ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane) : EMPTY_KEY;
         spec.key = EMPTY_KEY;
-        fetch_u8<LT, W, FULLW, true>(L, V, ws, q, q_norm, p.measure, words, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr, p.KBuild,
-                                     use_spec ? &spec : nullptr);
+        fetch_u8<LT, D32, true>(L, V, ws, q, q_norm, p.measure, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr, p.KBuild,
+                                use_spec ? &spec : nullptr);
       }
     }
     write_query_results(L, p, n);
@@ -365,10 +393,10 @@ __global__ void __launch_bounds__(128, G200_QUERY_MB_U8) query_kernel_u8(const _
   signal_exchange(p, total_warps);
 }
 
-template <class LT, int W, bool FULLW>
+template <class LT, int D32>
 static int launch_u8(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream)
 {
-  auto kern = query_kernel_u8<LT, W, FULLW>;
+  auto kern = query_kernel_u8<LT, D32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(query_kernel_u8)");
   kern<<<grid, a.warps_per_cta * 32, smem, stream>>>(a);
@@ -436,8 +464,8 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   if (p.base_type == GGNN_B200_BASE_U8) {
     // native uint8 rows: register lists (sorted_size <= 64), D a multiple of 16 (TMA rows) and <= 256 (exactness bound)
     // (a gather4 lands 4 rows = 4*D bytes at a 128-byte aligned shared-memory address: D % 32 == 0)
-    if (smem_lists || NS > 2 || p.D % 32 || p.D > 256)
-      return set_error(GGNN_B200_ERR_UNSUPPORTED, "native uint8 query: needs D % 32 == 0, D <= 256 and KQuery <= 47 (widen to fp32 otherwise)");
+    if (smem_lists || NS > 2 || !(p.D == 32 || p.D == 64 || p.D == 96 || p.D == 128 || p.D == 256))
+      return set_error(GGNN_B200_ERR_UNSUPPORTED, "native uint8 query: needs D in {32, 64, 96, 128, 256} and KQuery <= 47 (widen to fp32 otherwise)");
     if (make_row_gather_tensor_map_u8(&a.tmap, reinterpret_cast<const uint8_t*>(p.d_base), static_cast<uint64_t>(p.N_base), p.D))
       return GGNN_B200_ERR_UNSUPPORTED;
     const DeviceInfo& dev = device_info();
@@ -470,17 +498,17 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
       const uint32_t per_sm = std::max<uint32_t>(1, std::min<uint32_t>(G200_QUERY_MB_U8, dev.smem_per_sm / (smem + 1024)));
       grid = std::min(ctas_needed, per_sm * dev.num_sms);
     }
-    const bool fullw = (p.D % 128) == 0;
-    const int W = (p.D + 127) / 128;
-    switch (NS * 100 + W * 10 + (fullw ? 1 : 0)) {
-      case 111: return launch_u8<WarpLists<1>, 1, true>(a, grid, smem, stream);
-      case 110: return launch_u8<WarpLists<1>, 1, false>(a, grid, smem, stream);
-      case 121: return launch_u8<WarpLists<1>, 2, true>(a, grid, smem, stream);
-      case 120: return launch_u8<WarpLists<1>, 2, false>(a, grid, smem, stream);
-      case 211: return launch_u8<WarpLists<2>, 1, true>(a, grid, smem, stream);
-      case 210: return launch_u8<WarpLists<2>, 1, false>(a, grid, smem, stream);
-      case 221: return launch_u8<WarpLists<2>, 2, true>(a, grid, smem, stream);
-      case 220: return launch_u8<WarpLists<2>, 2, false>(a, grid, smem, stream);
+    switch (NS * 10 + p.D / 32) {  // the instantiated row lengths: 32, 64, 96, 128 and 256 bytes
+      case 11: return launch_u8<WarpLists<1>, 1>(a, grid, smem, stream);
+      case 12: return launch_u8<WarpLists<1>, 2>(a, grid, smem, stream);
+      case 13: return launch_u8<WarpLists<1>, 3>(a, grid, smem, stream);
+      case 14: return launch_u8<WarpLists<1>, 4>(a, grid, smem, stream);
+      case 18: return launch_u8<WarpLists<1>, 8>(a, grid, smem, stream);
+      case 21: return launch_u8<WarpLists<2>, 1>(a, grid, smem, stream);
+      case 22: return launch_u8<WarpLists<2>, 2>(a, grid, smem, stream);
+      case 23: return launch_u8<WarpLists<2>, 3>(a, grid, smem, stream);
+      case 24: return launch_u8<WarpLists<2>, 4>(a, grid, smem, stream);
+      case 28: return launch_u8<WarpLists<2>, 8>(a, grid, smem, stream);
     }
     return set_error(GGNN_B200_ERR_UNSUPPORTED, "no uint8 kernel variant");
   }

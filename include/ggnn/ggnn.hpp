@@ -8,7 +8,7 @@
 // Same names, argument meaning, defaults and error behaviour (std::runtime_error / std::out_of_range for API
 // misuse).  All computation happens in the sm_100a kernels behind the C ABI; there is no CPU fallback.
 // Differences: uint8 vectors stay uint8 on the device and are read natively by the traversal kernel where it
-// has a variant (D % 32 == 0, D <= 256, KQuery <= 47); the other kernels run on rows widened on the device for the duration
+// has a variant (D in {32, 64, 96, 128, 256}, KQuery <= 47); the other kernels run on rows widened on the device for the duration
 // of the call (bit-identical results, see ggnn_b200_widen_u8); multi-GPU results are merged on the first GPU by a kernel -- the traversal kernels store their
 // lists straight into its memory (peer access) -- instead of the reference's CPU heap merge, so results may stay on the
 // GPU for any number of GPUs; queryAsync() keeps several host batches in flight.  Shards that do not fit on their GPU
@@ -1172,11 +1172,12 @@ class GGNN {
       slot.base = Dataset<float>{};
     }
   }
-  /// does the traversal kernel read this slot's 1-byte rows natively for this query?  (include/ggnn_b200.h: D % 32 == 0,
-  /// D <= 256, KQuery <= 47)
+  /// does the traversal kernel read this slot's 1-byte rows natively for this query?  (include/ggnn_b200.h: D in {32, 64, 96, 128, 256},
+  /// KQuery <= 47)
   bool native_u8(const Slot& slot, const GenericDataset& query, uint32_t KQuery) const
   {
-    return slot.base_u8.data() && query.type == DataType::UINT8 && st->cfg.D % 32 == 0 && st->cfg.D <= 256 && KQuery <= 47 &&
+    const uint32_t D = st->cfg.D;
+    return slot.base_u8.data() && query.type == DataType::UINT8 && (D == 32 || D == 64 || D == 96 || D == 128 || D == 256) && KQuery <= 47 &&
            !std::getenv("GGNN_B200_NO_NATIVE_U8");
   }
 

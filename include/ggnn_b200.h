@@ -115,7 +115,7 @@ typedef struct {
    * base_type = GGNN_B200_BASE_U8, d_base and d_query point to uint8 rows of D bytes (a quarter of the gather traffic).
    * The reference computes every distance on static_cast<float>(value) (distance.cuh:104-148); for D <= 256 all
    * partial sums are integers below 2^24, i.e. exact in fp32, so integer arithmetic (dp4a) gives bit-identical
-   * distances.  Shapes the native kernel does not cover (it needs D % 32 == 0, D <= 256, KQuery <= 47) return
+   * distances.  Shapes the native kernel does not cover (it is built for D in {32, 64, 96, 128, 256} and needs KQuery <= 47) return
    * GGNN_B200_ERR_UNSUPPORTED (widen with
    * ggnn_b200_widen_u8 and use the fp32 path: identical results). */
   uint32_t base_type;
