@@ -339,18 +339,17 @@ struct WarpLists {
   // bit 3j = slot p may take over its predecessor's entry (p >= 1, p != BEST, p != head), bit 3j+1 = slot p has a
   // predecessor to compare with (p != 0, p != head), bit 3j+2 = p == BEST
   uint32_t lane_flags;
+  uint32_t static_flags;  // the same bits as if no slot of this lane were the head (they depend on BEST only)
   static constexpr uint32_t SORTED = 32u * NS;
 
+  // the head slot neither receives nor compares with its predecessor: clear bits 3j and 3j+1 of the register holding it
   __device__ __forceinline__ void update_flags()
   {
-    uint32_t f = 0;
+    const uint32_t lane = lane_id();
+    uint32_t f = static_flags;
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const uint32_t p = 32u * j + lane_id();
-      f |= ((p >= 1) && (p != BEST) && (p != head)) ? (1u << (3 * j)) : 0u;
-      f |= ((p != 0) && (p != head)) ? (2u << (3 * j)) : 0u;
-      f |= (p == BEST) ? (4u << (3 * j)) : 0u;
-    }
+    for (int j = 0; j < NS; ++j)
+      if (32u * j + lane == head) f &= ~(3u << (3 * j));
     lane_flags = f;
   }
 
@@ -358,11 +357,17 @@ struct WarpLists {
   {
     BEST = best;
     head = best;
+    uint32_t f = 0;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
       key[j] = EMPTY_KEY;
       dist[j] = G200_INF;
+      const uint32_t p = 32u * j + lane_id();
+      f |= ((p >= 1) && (p != best)) ? (1u << (3 * j)) : 0u;
+      f |= (p != 0) ? (2u << (3 * j)) : 0u;
+      f |= (p == best) ? (4u << (3 * j)) : 0u;
     }
+    static_flags = f;
     update_flags();
   }
   // common interface with SmemLists (the lists live in registers: no backing store needed)
