@@ -333,3 +333,36 @@ def test_dataset_load_ranges_and_errors(tmp_path):
     ggnn.UCharDataset(u).store(pb)
     assert os.path.getsize(pb) == 6 * (4 + 16)
     assert torch.equal(ggnn.UCharDataset.load(pb, 2, 3).tensor, u[2:5])
+
+
+def test_bench_query_blocks_are_prefix_stable():
+    """bench.gen_gpu draws queries in blocks of 10 000: the first blocks of a larger request equal a smaller request (the
+    batches of a bench step are different queries, batch 0 is the batch recall is quoted on)"""
+    import bench
+    dev = torch.device("cpu")
+    for kind in ("manifold8", "manifoldcos8", "uniform"):
+        _, q1 = bench.gen_gpu(64, 10_000, 16, kind, 1234, dev)
+        _, q3 = bench.gen_gpu(64, 25_000, 16, kind, 1234, dev)
+        assert q3.shape == (25_000, 16) and torch.equal(q3[:10_000], q1)
+        assert not torch.equal(q3[10_000:20_000], q1)
+    b1, _ = bench.gen_gpu(3000, 10, 16, "manifold8", 1234, dev, shard_index=2)
+    out = torch.empty((3000, 16))
+    b2, _ = bench.gen_gpu(3000, 10, 16, "manifold8", 1234, dev, shard_index=2, out=out)
+    assert b2.data_ptr() == out.data_ptr() and torch.equal(b1, b2)     # generated in place into a slice of a larger base
+    c1, c2 = bench.config1_data(), bench.config1_data()
+    assert torch.equal(c1[0], c2[0]) and torch.equal(c1[1], c2[1]) and c1[0].shape == (10_000, 128)
+
+
+def test_scatter_target_fills_the_exchange_fields():
+    """exchange.ScatterTarget -> ggnn_b200_query_params: no local result buffer, shard-local ids, slot = first slot of the
+    rank + shard index on the GPU"""
+    from ggnn_b200 import _lib
+    from ggnn_b200.exchange import ScatterTarget, _align
+    t = ScatterTarget(8, 6, 10_000, 3_200_000, 0x1000, 0x2000, 0x3000)
+    p = _lib.QueryParams()
+    p.d_query_results, p.shards_per_gpu, p.on_gpu_shard_id = 0x99, 4, 3
+    t.apply(p, 1)
+    assert p.d_query_results is None and p.d_query_results_dists is None
+    assert (p.shards_per_gpu, p.on_gpu_shard_id, p.n_scatter, p.scatter_slot, p.scatter_rows) == (1, 0, 8, 7, 10_000)
+    assert (p.scatter_dists_offset, p.d_scatter_dst, p.d_scatter_flags, p.d_scatter_done) == (3_200_000, 0x1000, 0x2000, 0x3000)
+    assert _align(1, 256) == 256 and _align(512, 256) == 512
