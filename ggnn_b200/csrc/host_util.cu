@@ -105,7 +105,7 @@ uint32_t env_u32(const char* name, uint32_t dflt)
 }  // namespace g200
 
 extern "C" const char* ggnn_b200_last_error(void) { return g200::g_err; }
-extern "C" const char* ggnn_b200_version(void) { return "ggnn_b200 0.1 (sm_100a; cp.async.bulk staged traversal)"; }
+extern "C" const char* ggnn_b200_version(void) { return "ggnn_b200 0.2 (sm_100a; TMA gather4 staged traversal, native uint8 rows, fused shard-merge exchange, tcgen05 brute force)"; }
 
 // uint8 -> fp32 widening (see ggnn_b200.h); 16 values per thread: one 16-byte load, four 16-byte stores
 namespace g200 {
