@@ -12,6 +12,9 @@
 
 namespace g200 {
 
+// 1.0f and -0.0f as values the compiler cannot see (dist8_fast, packed cosine path)
+static __constant__ float g200_fma_consts[2] = {1.0f, -0.0f};
+
 // per-warp shared-memory working set
 struct WarpSmem {
   float* stage;      // [stage_rows * D], 16-byte aligned
@@ -148,6 +151,34 @@ __device__ __forceinline__ float dist8_fast(const float* __restrict__ rows, int 
 #pragma unroll
     for (int w = 1; w < NW; ++w) tot = tot + warp_tree_sum8(v[w]);
     return tot;
+  }
+  if (NW == 1 && G200_PACKED_DIST) {
+    // one reference warp, cosine: the reference rounds every product and every sum separately (FMUL + FADD).  ptxas
+    // contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with explicit .rn (and with -fmad=false), so the two
+    // roundings are spelled as two FMAs that cannot be fused: a*b = fma(a, b, -0.0) and p + s = fma(p, 1.0, s), each
+    // correctly rounded exactly like the scalar instruction.  Rows (2p, 2p+1) advance together.
+    // (the two constants come from constant memory: as literals ptxas simplifies the FMAs back to mul / add -- and fuses them)
+    const float c_one = g200_fma_consts[0], c_neg0 = g200_fma_consts[1];
+    const uint64_t neg0 = pack2(c_neg0, c_neg0), one = pack2(c_one, c_one);
+    uint64_t ad[4] = {0ull, 0ull, 0ull, 0ull}, an[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int c = 0; c < D32; ++c) {
+      const uint64_t q2 = pack2(q[c], q[c]);
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const float* rp = rows + (2 * pr) * D + 32 * c + lane;
+        const uint64_t b2 = pack2(rp[0], rp[D]);
+        ad[pr] = fma2(fma2(b2, q2, neg0), one, ad[pr]);
+        an[pr] = fma2(fma2(b2, b2, neg0), one, an[pr]);
+      }
+    }
+    float vd[8], vn[8];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      unpack2(ad[pr], vd[2 * pr], vd[2 * pr + 1]);
+      unpack2(an[pr], vn[2 * pr], vn[2 * pr + 1]);
+    }
+    return cosine_finish(warp_tree_sum8(vd), warp_tree_sum8(vn), q_norm);
   }
   float dot_t = 0.f, nrm_t = 0.f;
 #pragma unroll
