@@ -707,6 +707,32 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
             del g8
     except Exception as e:  # noqa: BLE001
         ex["uint8_native"] = {"error": repr(e)[-300:]}
+    # opt-in interleaved copy of the fp32 base (GGNN_B200_INTERLEAVED_BASE=1): one 16-byte shared-memory load per lane and
+    # row instead of four 4-byte loads, same results, twice the memory of the base
+    try:
+        st2 = [torch.cuda.Stream(dev) for _ in range(2)]
+
+        def piped32(n=20):
+            for i in range(n):
+                with torch.cuda.stream(st2[i % 2]):
+                    idx.query(query, K, a.tau_query, a.max_iterations)
+            for s_ in st2:
+                torch.cuda.current_stream(dev).wait_stream(s_)
+        (r_nat, d_nat), ms_nat = timed(lambda: idx.query(query, K, a.tau_query, a.max_iterations), reps=15)
+        _, p_nat = timed(piped32, reps=3)
+        os.environ["GGNN_B200_INTERLEAVED_BASE"] = "1"
+        try:
+            (r_il, d_il), ms_il = timed(lambda: idx.query(query, K, a.tau_query, a.max_iterations), reps=15)
+            _, p_il = timed(piped32, reps=3)
+        finally:
+            del os.environ["GGNN_B200_INTERLEAVED_BASE"]
+            idx._shards[0].base_il = None
+        ex["interleaved_base"] = {"what": "GGNN_B200_INTERLEAVED_BASE=1: second copy of the fp32 base with a lane's four dims adjacent (LDS.128)",
+                                  "single_batch_ms": ms_il, "natural_single_batch_ms": ms_nat, "pipelined_ms_per_batch": p_il / 20,
+                                  "natural_pipelined_ms_per_batch": p_nat / 20, "results_identical": bool(torch.equal(r_il, r_nat) and torch.equal(d_il, d_nat)),
+                                  "extra_bytes": int(base.numel() * 4)}
+    except Exception as e:  # noqa: BLE001
+        ex["interleaved_base"] = {"error": repr(e)[-300:]}
     # a harder data set (intrinsic dimension 16): operating point found by sweeping the REFERENCE first
     # (profiles/r02_reference_sweep_manifold16.json, procedure of ggnn_benchmark.cpp:186-200)
     try:

@@ -43,6 +43,7 @@ class QueryParams(C.Structure):
         ("scatter_dists_offset", C.c_size_t), ("d_scatter_dst", C.c_void_p), ("d_scatter_flags", C.c_void_p),
         ("d_scatter_done", C.c_void_p),
         ("base_type", C.c_uint32),   # 0 fp32, 1 native uint8 rows (d_base / d_query are uint8 then)
+        ("d_base_interleaved", C.c_void_p),   # optional interleaved copy of an fp32 base (ggnn_b200_interleave_rows)
     ]
 
 
@@ -67,7 +68,7 @@ EXPORTS = [
     "ggnn_b200_merge_topk", "ggnn_b200_widen_u8",
     "ggnn_b200_ipc_alloc", "ggnn_b200_ipc_open", "ggnn_b200_ipc_close", "ggnn_b200_ipc_free", "ggnn_b200_peer_enable",
     "ggnn_b200_wait_flag", "ggnn_b200_refine_graph", "ggnn_b200_rng_create", "ggnn_b200_rng_fill_build", "ggnn_b200_rng_destroy",
-    "ggnn_b200_build_stats_begin", "ggnn_b200_build_stats_end",
+    "ggnn_b200_build_stats_begin", "ggnn_b200_build_stats_end", "ggnn_b200_interleave_rows",
 ]
 
 _lib = None
@@ -120,6 +121,7 @@ def lib():
         l.ggnn_b200_rng_fill_build.argtypes = [vp, cfgp, vp, vp]
         l.ggnn_b200_rng_destroy.argtypes = [vp]
         l.ggnn_b200_rng_destroy.restype = None
+        l.ggnn_b200_interleave_rows.argtypes = [vp, vp, u32, u32, vp]
         l.ggnn_b200_build_stats_begin.argtypes = []
         l.ggnn_b200_build_stats_end.argtypes = [C.POINTER(BuildPassStats), u32, C.POINTER(u32)]
         _lib = l

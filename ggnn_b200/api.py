@@ -90,6 +90,7 @@ class _Shard:
         self.base = base          # [N_shard, D] fp32 on `device` (None in swap mode: see ggnn_b200/swap.py; None for a
                                   # uint8 base until a kernel needs widened rows: GGNN._f32)
         self.base_u8 = None       # [N_shard, D] uint8 on `device`: native rows of a uint8 base (resident mode)
+        self.base_il = None       # optional interleaved copy of fp32 rows (GGNN_B200_INTERLEAVED_BASE=1, see _interleaved)
         self.global_id = global_id
         self.graph = None         # Graph (resident mode)
         self.pool = pool          # swap.ShardPool of this shard's GPU, or None = everything stays resident
@@ -237,6 +238,18 @@ class GGNN:
                 _lib.check(_lib.lib().ggnn_b200_widen_u8(_ptr(sh.base_u8), _ptr(out), sh.base_u8.numel(), _stream_ptr(sh.device)))
             sh.base = out
         return sh.base
+
+    def _interleaved(self, sh, sh_base):
+        """GGNN_B200_INTERLEAVED_BASE=1: a second copy of a resident fp32 shard whose rows hold element 32c + t at 4t + c
+        (ggnn_b200_interleave_rows), so that the traversal kernel reads a lane's four dims with one 16-byte load.  Same
+        results; doubles the memory of the base, hence opt-in.  D = 128 only."""
+        if sh.base_il is None:
+            with torch.cuda.device(sh.device):
+                out = torch.empty_like(sh_base)
+                _lib.check(_lib.lib().ggnn_b200_interleave_rows(_ptr(sh_base), _ptr(out), sh_base.shape[0], sh_base.shape[1],
+                                                                _stream_ptr(sh.device)))
+            sh.base_il = out
+        return sh.base_il
 
     @staticmethod
     def _drop_f32(sh):
@@ -395,6 +408,9 @@ class GGNN:
                         if q_f32 is None:
                             q_f32 = q_dev.float()
                     p.d_base, p.d_query = sh_base.data_ptr(), (q_f32 if q_f32 is not None else q_dev).data_ptr()
+                    if (sh.pool is None and sh.base_u8 is None and cfg.D == 128 and int(measure) == 0 and
+                            os.environ.get("GGNN_B200_INTERLEAVED_BASE")):
+                        p.d_base_interleaved = self._interleaved(sh, sh_base).data_ptr()
                 p.d_graph = sh_graph.graph.data_ptr()
                 p.d_starting_points = sh_graph.layer_translation(_lib.L - 1).data_ptr()
                 p.d_nn1_stats = sh_graph.nn1_stats.data_ptr()

@@ -142,3 +142,26 @@ extern "C" int ggnn_b200_widen_u8(const uint8_t* d_src, float* d_dst, size_t cou
   g200::widen_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(d_src, d_dst, count);
   return g200::set_cuda_error(cudaGetLastError(), "widen_u8_kernel launch");
 }
+
+// interleaved copy of an fp32 base (see ggnn_b200.h): one warp per row, coalesced loads, D/32 adjacent values per lane
+namespace g200 {
+__global__ void __launch_bounds__(256) interleave_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, uint32_t N, uint32_t D32)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  for (size_t n = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); n < N; n += static_cast<size_t>(gridDim.x) * 8) {
+    const float* r = src + n * 32 * D32;
+    float* w = dst + n * 32 * D32 + static_cast<size_t>(D32) * lane;
+    for (uint32_t c = 0; c < D32; ++c) w[c] = r[32 * c + lane];
+  }
+}
+}  // namespace g200
+
+extern "C" int ggnn_b200_interleave_rows(const float* d_src, float* d_dst, uint32_t N, uint32_t D, ggnn_b200_stream_t stream_)
+{
+  if (!d_src || !d_dst) return g200::set_error(GGNN_B200_ERR_INVALID, "null device pointer");
+  if (D == 0 || D % 32 || D > 128) return g200::set_error(GGNN_B200_ERR_UNSUPPORTED, "interleaved rows need D in {32, 64, 96, 128}");
+  if (!N) return 0;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((static_cast<size_t>(N) + 7) / 8, static_cast<size_t>(g200::device_info().num_sms) * 16));
+  g200::interleave_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(d_src, d_dst, N, D / 32);
+  return g200::set_cuda_error(cudaGetLastError(), "interleave_rows_kernel launch");
+}

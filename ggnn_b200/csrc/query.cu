@@ -76,7 +76,7 @@ __device__ __forceinline__ void signal_exchange(const ggnn_b200_query_params& p,
 }
 
 // LT = WarpLists<NS> (best list + prioQ in registers, sorted_size <= 256) or SmemLists (anything larger)
-template <class LT, bool FAST, int NI, bool G4 = false>
+template <class LT, bool FAST, int NI, bool G4 = false, bool IL = false>
 __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) query_kernel(const __grid_constant__ QueryArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) qu
     // query_layer.cu:55 fetch_unfiltered(d_starting_points, nullptr, S)
     for (uint32_t i = 0; i < p.num_starting_points; i += 32) {
       const int ck = (i + lane < p.num_starting_points) ? p.d_starting_points[i + lane] : EMPTY_KEY;
-      fetch<LT, FAST, NI, 1, false, G4>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st, a.prefetch ? p.d_graph : nullptr,
+      fetch<LT, FAST, NI, 1, false, G4, IL>(L, V, ws, qv, p.d_base, nullptr, ck, xi, st, a.prefetch ? p.d_graph : nullptr,
                                     p.KBuild);
     }
 
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) qu
         else
           ck = (i + lane < p.KBuild) ? __ldg(p.d_graph + static_cast<size_t>(anchor) * p.KBuild + i + lane) : EMPTY_KEY;
         spec.key = EMPTY_KEY;
-        fetch<LT, FAST, NI, 1, true, G4>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
+        fetch<LT, FAST, NI, 1, true, G4, IL>(L, V, ws, qv, p.d_base, nullptr, ck, r_xi, st, a.prefetch ? p.d_graph : nullptr,
                                      p.KBuild, use_spec ? &spec : nullptr);
       }
     }
@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(128, G4 ? G200_QUERY_MB_G4 : G200_QUERY_MB) qu
   signal_exchange(p, total_warps);
 }
 
-template <class LT, bool FAST, int NI, bool G4 = false>
+template <class LT, bool FAST, int NI, bool G4 = false, bool IL = false>
 static int launch(const QueryArgs& a, int grid, size_t smem, cudaStream_t stream)
 {
-  auto kern = query_kernel<LT, FAST, NI, G4>;
+  auto kern = query_kernel<LT, FAST, NI, G4, IL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(query_kernel)");
   kern<<<grid, a.warps_per_cta * 32, smem, stream>>>(a);
@@ -542,11 +542,14 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
   rows = env_u32("GGNN_B200_QUERY_STAGE_ROWS", rows);
   if (rows % 8 || rows == 0 || rows > 32) return set_error(GGNN_B200_ERR_INVALID, "stage rows must be 8, 16, 24 or 32");
   // rows must be 16-byte multiples to be staged; default: TMA gather4 (3) where a variant exists, else one bulk copy per row (0)
+  bool use_il = false;
   a.stage_mode = (p.D % 4) ? 2u : env_u32("GGNN_B200_STAGE_MODE", 3);
   if (a.stage_mode == 3) {  // TMA tile::gather4 row staging: register-resident fast kernels with pipelined 8-row groups only
     if (fast && rows >= 16 && (NI == 3 || NI == 4)) {  // the instantiated gather4 variants (two 8-row buffers)
       // (a driver without cuTensorMapEncodeTiled: stay with one bulk copy per row)
-      if (make_row_gather_tensor_map(&a.tmap, p.d_base, static_cast<uint64_t>(p.N_base), p.D) == 0) {
+      // (interleaved copy of the base, if the caller has one: same shape, rows permuted internally)
+      use_il = p.d_base_interleaved && NI == 4 && p.measure == GGNN_B200_EUCLIDEAN;
+      if (make_row_gather_tensor_map(&a.tmap, use_il ? p.d_base_interleaved : p.d_base, static_cast<uint64_t>(p.N_base), p.D) == 0) {
         rows = 16;
         a.pad_row = env_u32("GGNN_B200_GATHER4_PAD_VALID", 0) ? 0 : p.N_base;  // out of bounds: zero fill, no memory traffic
       }
@@ -586,6 +589,10 @@ extern "C" int ggnn_b200_query(const ggnn_b200_query_params* pin, uint32_t N_que
 
 #define G200_LAUNCH(NS_, FAST_, NI_) return launch<WarpLists<NS_>, FAST_, NI_>(a, grid, smem, stream)
   if (smem_lists) return launch<SmemLists, false, 1>(a, grid, smem, stream);
+  if (a.stage_mode == 3 && use_il) {
+    if (NS == 1) return launch<WarpLists<1>, true, 4, true, true>(a, grid, smem, stream);
+    return launch<WarpLists<2>, true, 4, true, true>(a, grid, smem, stream);
+  }
   if (a.stage_mode == 3) {
     switch (NS * 10 + NI) {
       case 13: return launch<WarpLists<1>, true, 3, true>(a, grid, smem, stream);

@@ -76,12 +76,33 @@ struct Stats {
 // (4 dims per thread): virtual thread (w, lane) owns the 32-float chunks c = w, w+NW, w+2NW, ...
 // (dims 32*c + lane), accumulated in that order; each virtual warp w is tree-reduced, the warp
 // aggregates are added sequentially (cub::BlockReduce).  Lane l gets row (l & 7).
-template <int D32, int NW>
+template <int D32, int NW, bool IL = false>
 __device__ __forceinline__ float dist8_fast(const float* __restrict__ rows, int nrows, int measure,
                                             const float (&q)[D32], float q_norm)
 {
   const int lane = lane_id();
   constexpr int D = 32 * D32;
+  if constexpr (IL && D32 == 4 && NW == 1) {
+    // interleaved rows (ggnn_b200_interleave_rows), Euclidean: this lane's dims lane, lane+32, lane+64, lane+96 of a row are
+    // ONE 16-byte load; the FMA chain runs over them in the same order, rows (2p, 2p+1) together in packed fp32
+    const float4* r4 = reinterpret_cast<const float4*>(rows) + lane;
+    const uint64_t q0 = pack2(q[0], q[0]), q1 = pack2(q[1], q[1]), q2 = pack2(q[2], q[2]), q3 = pack2(q[3], q[3]);
+    float v[8];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+      const float4 a = r4[(2 * pr) * (D / 4)], b = r4[(2 * pr + 1) * (D / 4)];
+      uint64_t d = sub2(pack2(a.x, b.x), q0);
+      uint64_t acc = fma2(d, d, 0ull);
+      d = sub2(pack2(a.y, b.y), q1);
+      acc = fma2(d, d, acc);
+      d = sub2(pack2(a.z, b.z), q2);
+      acc = fma2(d, d, acc);
+      d = sub2(pack2(a.w, b.w), q3);
+      acc = fma2(d, d, acc);
+      unpack2(acc, v[2 * pr], v[2 * pr + 1]);
+    }
+    return warp_tree_sum8(v);
+  }
   if (measure == 0 && NW == 1 && G200_PACKED_DIST) {
     // one reference warp, Euclidean: rows (2p, 2p+1) advance together in packed fp32 (per element the same
     // sub.rn + fma.rn chain over dims lane, lane+32, ... as the scalar code).  Always the whole group: rows >= nrows
@@ -367,7 +388,7 @@ __device__ __forceinline__ void finish_fetch(LT& L, int key_r, float mine, int c
   }
 }
 
-template <class LT, bool FAST, int D32, int NW, bool FILTER, bool G4 = false>
+template <class LT, bool FAST, int D32, int NW, bool FILTER, bool G4 = false, bool IL = false>
 __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
                                       const QueryVec<FAST, D32, NW>& qv, const float* __restrict__ base,
                                       const int* __restrict__ translation, int ck, float xi, Stats& st,
@@ -426,7 +447,7 @@ __device__ __forceinline__ void fetch(LT& L, const VisitedSet& V, WarpSmem& ws,
       const int buf = g & 1;
       mbar_wait_s(bar_s + 8u * buf, (ws.parity >> buf) & 1u);
       ws.parity ^= 1u << buf;
-      const float dg = dist8_fast<D32, NW>(ws.stage + buf * 8 * D, min(8, cnt - 8 * g), qv.cfg.measure, qv.q, qv.q_norm);
+      const float dg = dist8_fast<D32, NW, IL>(ws.stage + buf * 8 * D, min(8, cnt - 8 * g), qv.cfg.measure, qv.q, qv.q_norm);
       if ((lane >> 3) == g) mine = dg;
       __syncwarp();  // the group's rows have been read: its buffer may be refilled
       if (g + 2 < ngroups) {

@@ -119,6 +119,11 @@ typedef struct {
    * GGNN_B200_ERR_UNSUPPORTED (widen with
    * ggnn_b200_widen_u8 and use the fp32 path: identical results). */
   uint32_t base_type;
+  /* --- optional interleaved copy of an fp32 base (ggnn_b200_interleave_rows; D = 128, Euclidean, register-resident
+   * lists): row n holds element 32c + t at position 4t + c, so that the four elements a lane accumulates in the
+   * reference's order (dims t, t+32, t+64, t+96; distance.cuh:104-139) are ONE 16-byte shared-memory load.  Same results;
+   * costs a second copy of the base.  NULL = rows are read in their natural layout. */
+  const float* d_base_interleaved;
 } ggnn_b200_query_params;
 #define GGNN_B200_BASE_F32 0
 #define GGNN_B200_BASE_U8 1
@@ -241,6 +246,10 @@ int ggnn_b200_ipc_free(void* d_ptr);
 int ggnn_b200_peer_enable(int peer_device);
 int ggnn_b200_wait_flag(const uint32_t* d_flag, uint32_t expected, uint32_t timeout_ms, uint32_t* d_timed_out,
                         ggnn_b200_stream_t stream);
+
+/* d_dst[n][(D/32) * t + c] = d_src[n][32 * c + t] for t < 32, c < D/32 (D a multiple of 32, D <= 128): the layout of
+ * ggnn_b200_query_params.d_base_interleaved */
+int ggnn_b200_interleave_rows(const float* d_src, float* d_dst, uint32_t N, uint32_t D, ggnn_b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * uint8 base / query vectors (the reference's BaseT = uint8_t instantiation, include/ggnn/base/lib.h:26-28).

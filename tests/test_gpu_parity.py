@@ -1058,3 +1058,50 @@ def test_gpu_resident_tensors_are_used_in_place():
     gs.set_base(b)
     gs._prepare(24)
     assert [sh.base.data_ptr() for sh in gs._shards] == [b.data_ptr(), b[10000:].data_ptr()]
+
+
+def test_interleaved_base_copy_gives_identical_results(monkeypatch):
+    """ggnn_b200_query_params.d_base_interleaved (ggnn_b200_interleave_rows: element 32c + t of a row at 4t + c, one
+    16-byte shared-memory load per lane and row instead of four 4-byte loads): ids, distances and the pop / distance
+    counters equal the natural layout's and the oracle's, for both list sizes"""
+    base, query = gen_data(6000, 400, 128, seed=31)
+    cfg = O.graph_config(6000, 128, 24)
+    u = np.random.default_rng(5).random(6000 + 1500 + 2000, dtype=np.float32) * 0.999 + 0.0005
+    gr = O.build_graph(cfg, base, 0.5, u, 1, 0)
+    b = dev(base)
+    b_il = torch.empty_like(b)
+    _lib.check(_lib.lib().ggnn_b200_interleave_rows(ptr(b), ptr(b_il), 6000, 128, stream()))
+    torch.cuda.synchronize()
+    exp = base.reshape(6000, 4, 32).transpose(0, 2, 1).reshape(6000, 128)          # [n][t][c]
+    assert np.array_equal(b_il.cpu().numpy(), exp)
+    q, g0 = dev(query), dev(gr.layer_graph(0))
+    sp, ns = dev(gr.start_points()), dev(gr.nn1_stats)
+    for K, max_it in ((10, 400), (10, 200)):                                       # sorted_size 32 / 64
+        o_ids, o_d, o_st = O.query(base, query, gr.layer_graph(0), gr.start_points(), gr.nn1_stats, K, 0.7, max_it, 0,
+                                   with_stats=True)
+        for il in (False, True):
+            ids = torch.full((400, K), -5, dtype=torch.int32, device="cuda")
+            dists = torch.full((400, K), -5.0, dtype=torch.float32, device="cuda")
+            st = torch.zeros((400, 2), dtype=torch.int32, device="cuda")
+            wc = torch.zeros(1, dtype=torch.int32, device="cuda")
+            p = _lib.QueryParams()
+            p.D, p.measure, p.KQuery, p.tau_query, p.max_iterations = 128, 0, K, 0.7, max_it
+            p.N_base, p.KBuild, p.num_starting_points = 6000, 24, gr.start_points().size
+            p.d_base, p.d_query, p.d_graph = b.data_ptr(), q.data_ptr(), g0.data_ptr()
+            p.d_starting_points, p.d_nn1_stats = sp.data_ptr(), ns.data_ptr()
+            p.d_query_results, p.d_query_results_dists, p.d_stats = ids.data_ptr(), dists.data_ptr(), st.data_ptr()
+            p.shards_per_gpu, p.on_gpu_shard_id, p.d_work_counter = 1, 0, wc.data_ptr()
+            p.d_base_interleaved = b_il.data_ptr() if il else None
+            _lib.check(_lib.lib().ggnn_b200_query(C.byref(p), 400, stream()))
+            torch.cuda.synchronize()
+            assert np.array_equal(ids.cpu().numpy(), o_ids) and np.array_equal(dists.cpu().numpy(), o_d), (K, max_it, il)
+            assert np.array_equal(st.cpu().numpy().astype(np.uint32), o_st)
+    # through the Python API (opt-in by environment variable)
+    g = ggnn.GGNN()
+    g.set_return_results_on_gpu(True)
+    g.set_base(b)
+    g.build(24, 0.5)
+    r0 = g.query(q, 10, 0.64, 400)
+    monkeypatch.setenv("GGNN_B200_INTERLEAVED_BASE", "1")
+    r1 = g.query(q, 10, 0.64, 400)
+    assert g._shards[0].base_il is not None and torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1])
