@@ -704,6 +704,18 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
                                   "results_identical_to_fp32": bool(torch.equal(i8, i32) and torch.equal(d8, d32)),
                                   "algorithmic_bytes_per_launch": alg8, "fp32_algorithmic_bytes_per_launch": alg32,
                                   "base_bytes": int(base.numel()), "fp32_base_bytes": int(base.numel() * 4)}
+            # ... and bf_query on the uint8 rows: exact integer contraction on the int8 tensor cores (csrc/bf_i8.cu)
+            try:
+                (b8i, b8d), ms_bf8 = timed(lambda: g8.bf_query(q8, K), reps=3)
+                (b8i100, _), ms_bf8_100 = timed(lambda: g8.bf_query(q8, 100), reps=3)
+                ex["bf_query_uint8"] = {"what": f"{a.n_base}x{a.dim} uint8 base, {Nq} queries: tcgen05.mma.kind::i8 (u8 x u8 -> s32, exact) "
+                                                "+ integer re-rank, rows never widened",
+                                        "k10_ms": ms_bf8, "k100_ms": ms_bf8_100,
+                                        "k10_useful_tops": 2.0 * Nq * a.n_base * a.dim / (ms_bf8 * 1e-3) / 1e12,
+                                        "ids_identical_to_fp32_bf_query": bool(torch.equal(b8i, gt)),
+                                        "ids_crc32_k10": _crc(b8i), "ids_crc32_k100": _crc(b8i100)}
+            except Exception as e:  # noqa: BLE001
+                ex["bf_query_uint8"] = {"error": repr(e)[-300:]}
             del g8
     except Exception as e:  # noqa: BLE001
         ex["uint8_native"] = {"error": repr(e)[-300:]}

@@ -69,6 +69,7 @@ EXPORTS = [
     "ggnn_b200_ipc_alloc", "ggnn_b200_ipc_open", "ggnn_b200_ipc_close", "ggnn_b200_ipc_free", "ggnn_b200_peer_enable",
     "ggnn_b200_wait_flag", "ggnn_b200_refine_graph", "ggnn_b200_rng_create", "ggnn_b200_rng_fill_build", "ggnn_b200_rng_destroy",
     "ggnn_b200_build_stats_begin", "ggnn_b200_build_stats_end", "ggnn_b200_interleave_rows",
+    "ggnn_b200_bf_query_u8", "ggnn_b200_bf_query_u8_workspace_bytes", "ggnn_b200_debug_i8_pack", "ggnn_b200_debug_i8_mma",
 ]
 
 _lib = None
@@ -122,6 +123,11 @@ def lib():
         l.ggnn_b200_rng_destroy.argtypes = [vp]
         l.ggnn_b200_rng_destroy.restype = None
         l.ggnn_b200_interleave_rows.argtypes = [vp, vp, u32, u32, vp]
+        l.ggnn_b200_bf_query_u8.argtypes = [C.POINTER(BfQueryParams), u32, vp]
+        l.ggnn_b200_bf_query_u8_workspace_bytes.restype = C.c_size_t
+        l.ggnn_b200_bf_query_u8_workspace_bytes.argtypes = [u32, i32, u32, u32, u32]
+        l.ggnn_b200_debug_i8_pack.argtypes = [vp, u32, u32, u32, vp, vp, vp]
+        l.ggnn_b200_debug_i8_mma.argtypes = [vp, vp, u32, vp, vp]
         l.ggnn_b200_build_stats_begin.argtypes = []
         l.ggnn_b200_build_stats_end.argtypes = [C.POINTER(BuildPassStats), u32, C.POINTER(u32)]
         _lib = l

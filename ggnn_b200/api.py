@@ -556,6 +556,16 @@ class GGNN:
         dev = torch.device("cuda", self._gpus[0])
         with torch.cuda.device(dev):
             single = self._shards[0] if (self._shards and len(self._shards) == 1 and self._shards[0].pool is None) else None
+            # uint8 base: exact integer contraction on the int8 tensor cores, rows never widened (GGNN_B200_NO_I8_BF=1:
+            # widen and take the fp32 path instead -- identical results)
+            ws_u8 = 0
+            if query.dtype == torch.uint8 and not os.environ.get("GGNN_B200_NO_I8_BF"):
+                ws_u8 = _lib.lib().ggnn_b200_bf_query_u8_workspace_bytes(self._base.shape[1], int(measure), int(k_gt),
+                                                                         self._base.shape[0], query.shape[0])
+            if ws_u8:
+                rows = single.base_u8 if (single is not None and single.base_u8 is not None) else self._base.to(dev).contiguous()
+                ids, dists = self._bf_query_rows(rows, query.to(dev).contiguous(), int(k_gt), int(measure))
+                return (ids, dists) if self._results_on_gpu else (ids.cpu(), dists.cpu())
             if single is not None:
                 base = self._f32(single)
             else:
@@ -583,10 +593,14 @@ class GGNN:
             p.d_base, p.d_query = base.data_ptr(), q.data_ptr()
             p.d_query_results, p.d_query_results_dists = ids.data_ptr(), dists.data_ptr()
             # scratch for the tensor-core contraction path (0 = shape not covered -> exact SIMT scan)
-            ws_bytes = l.ggnn_b200_bf_query_workspace_bytes(base.shape[1], int(measure), int(k_gt), base.shape[0], Nq)
+            u8 = base.dtype == torch.uint8  # native uint8 rows: ggnn_b200_bf_query_u8 (the caller checked the shape)
+            if u8 and q.dtype != torch.uint8:
+                raise ValueError("query data type has to match base data type")
+            size_fn = l.ggnn_b200_bf_query_u8_workspace_bytes if u8 else l.ggnn_b200_bf_query_workspace_bytes
+            ws_bytes = size_fn(base.shape[1], int(measure), int(k_gt), base.shape[0], Nq)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
             p.d_workspace, p.workspace_bytes = (ws.data_ptr() if ws is not None else None), ws_bytes
-            _lib.check(l.ggnn_b200_bf_query(C.byref(p), Nq, _stream_ptr(dev)))
+            _lib.check((l.ggnn_b200_bf_query_u8 if u8 else l.ggnn_b200_bf_query)(C.byref(p), Nq, _stream_ptr(dev)))
             if ws is not None:
                 ws.record_stream(torch.cuda.current_stream(dev))
         return ids, dists

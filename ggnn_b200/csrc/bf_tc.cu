@@ -25,6 +25,8 @@
 // A query whose candidate list overflows is re-done by the exact SIMT scan, so the result never depends on the
 // candidate capacity.
 #include "traverse.cuh"
+#include "umma.cuh"
+#include "bf_tc_host.h"
 #include "host_util.h"
 #include "../../include/ggnn_b200.h"
 
@@ -41,88 +43,6 @@ constexpr int TC_STAGES = 2;   // B ring depth (each stage = hi + lo k-block = 3
 constexpr int TC_KP = 128;     // max K of the tensor path (per-row best lists in shared memory: 32 or 128 slots)
 constexpr int TC_THREADS = 384;  // warps 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue (2 per TMEM lane quarter)
 constexpr uint32_t TC_KBLOCK_BYTES = TC_BM * TC_BK * 4;  // 16 KB
-
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr)
-{
-  // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused;
-  // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
-  const uint32_t addr = smem_u32(smem_ptr);
-  uint64_t d = static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1024u >> 4) << 32;
-  d |= 1ull << 46;
-  d |= 2ull << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// A operand from tensor memory (128 lanes = rows, one 32-bit column per tf32 K element), B from shared memory
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_c), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
-{
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
-{
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4])
-{
-  uint32_t r[4];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ---- stage 1: split + norms ---------------------------------------------------------------------
 // one warp per row; out rows padded with zeros up to n_rows_pad (TMA never reads past them anyway)
@@ -507,63 +427,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
 }
 
 // ---- stage 3: exact re-rank ----------------------------------------------------------------------
-// sorted K-best by (dist, id) lexicographic order, insertion in any order
-template <int NSK>
-struct LexKBest {
-  int id[NSK];
-  float dist[NSK];
-  __device__ __forceinline__ void init()
-  {
-#pragma unroll
-    for (int j = 0; j < NSK; ++j) {
-      id[j] = 0x7fffffff;
-      dist[j] = G200_INF;
-    }
-  }
-  __device__ __forceinline__ static bool less(float d, int i, float d2, int i2) { return d < d2 || (d == d2 && i < i2); }
-  __device__ __forceinline__ void worst(uint32_t K, float& d, int& i) const
-  {
-    float v = dist[0];
-    int w = id[0];
-#pragma unroll
-    for (int j = 1; j < NSK; ++j) {
-      v = ((K - 1) >> 5) == j ? dist[j] : v;
-      w = ((K - 1) >> 5) == j ? id[j] : w;
-    }
-    d = __shfl_sync(FULL, v, (K - 1) & 31);
-    i = __shfl_sync(FULL, w, (K - 1) & 31);
-  }
-  __device__ __forceinline__ void add(float d, int i)
-  {
-    const int lane = lane_id();
-    int nid[NSK];
-    float nd[NSK];
-#pragma unroll
-    for (int j = 0; j < NSK; ++j) {
-      int pi = __shfl_up_sync(FULL, id[j], 1);
-      float pd = __shfl_up_sync(FULL, dist[j], 1);
-      if (j > 0) {
-        const int ci = __shfl_sync(FULL, id[j - 1], 31);
-        const float cd = __shfl_sync(FULL, dist[j - 1], 31);
-        if (lane == 0) {
-          pi = ci;
-          pd = cd;
-        }
-      }
-      const bool first = (j == 0 && lane == 0);
-      const bool shift_in = !first && less(d, i, pd, pi);
-      const bool ins = less(d, i, dist[j], id[j]) && (first || !less(d, i, pd, pi));
-      nid[j] = ins ? i : (shift_in ? pi : id[j]);
-      nd[j] = ins ? d : (shift_in ? pd : dist[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < NSK; ++j) {
-      id[j] = nid[j];
-      dist[j] = nd[j];
-    }
-  }
-};
-
 struct TcRerankArgs {
   ggnn_b200_bf_query_params p;
   uint32_t N_query, cap, warp_smem_bytes;
@@ -680,7 +543,6 @@ struct TcWorkspace {
   int32_t* cand;
   size_t total;
 };
-constexpr uint32_t TC_MAX_SPLITS = 32;  // 64 published best lists per query
 static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, uint32_t cap, uint32_t K)
 {
   char* b = static_cast<char*>(basep);
@@ -712,7 +574,7 @@ static TcWorkspace tc_layout(void* basep, uint32_t N, uint32_t Nq, uint32_t D, u
 // exactly, the capacity only affects speed.
 constexpr uint32_t TC_CAP_MIN = 1024, TC_CAP_MAX = 8192, TC_CAND_PER_SPLIT = 192;
 
-static uint32_t tc_cap(uint32_t Nq)
+uint32_t tc_cap(uint32_t Nq)
 {
   // keep the candidate buffer below ~256 MB
   const uint64_t by_mem = (256ull << 20) / (static_cast<uint64_t>(std::max(1u, Nq)) * 4);
@@ -720,7 +582,7 @@ static uint32_t tc_cap(uint32_t Nq)
 }
 
 // number of base splits: fill the SMs (one 209 KB CTA each) in whole waves, within the candidate capacity
-static uint32_t tc_pick_splits(uint32_t q_tiles, uint32_t n_tiles, uint32_t num_sms, uint32_t cap, uint32_t K)
+uint32_t tc_pick_splits(uint32_t q_tiles, uint32_t n_tiles, uint32_t num_sms, uint32_t cap, uint32_t K)
 {
   const uint32_t forced = env_u32("GGNN_B200_BF_SPLITS", 0);
   const uint32_t per_split = std::max(TC_CAND_PER_SPLIT, 20u * K);  // ~2 lists x K (1 + ln(rows / K)) per split

@@ -986,6 +986,37 @@ class GGNN {
     Dataset<float> b_dev;
     const float* db = nullptr;
     Slot* single = (s.shards.size() == 1 && s.shards[0].slot >= 0) ? &s.gpus[0].slots[s.shards[0].slot] : nullptr;
+    // uint8 base: exact integer contraction on the int8 tensor cores (ggnn_b200_bf_query_u8), rows never widened
+    // (GGNN_B200_NO_I8_BF=1: widen and take the fp32 path instead -- identical results)
+    if (s.base->type == DataType::UINT8 && query.type == DataType::UINT8 && !std::getenv("GGNN_B200_NO_I8_BF")) {
+      const size_t ws_bytes = ggnn_b200_bf_query_u8_workspace_bytes(s.base->D, static_cast<int>(measure), KGT, static_cast<uint32_t>(s.base->N),
+                                                                    static_cast<uint32_t>(query.N));
+      if (ws_bytes) {
+        Dataset<uint8_t> b8_dev;
+        const uint8_t* b8 = nullptr;
+        if (single && single->base_u8.data()) b8 = single->base_u8.data();
+        else {
+          b8_dev = u8_on_gpu(*s.base, gpu, nullptr);
+          b8 = b8_dev.data();
+        }
+        Dataset<uint8_t> q8 = u8_on_gpu(query, gpu, nullptr);
+        Results out;
+        out.ids = Dataset<KeyT>::emptyOnGPU(query.N, KGT, gpu);
+        out.dists = Dataset<ValueT>::emptyOnGPU(query.N, KGT, gpu);
+        ggnn_b200_bf_query_params p{};
+        p.D = s.base->D; p.measure = static_cast<int>(measure); p.KQuery = KGT; p.N_base = static_cast<int32_t>(s.base->N);
+        p.d_base = reinterpret_cast<const float*>(b8); p.d_query = reinterpret_cast<const float*>(q8.data());
+        p.d_query_results = out.ids.data(); p.d_query_results_dists = out.dists.data();
+        p.workspace_bytes = ws_bytes;
+        detail::cuda_check(cudaMalloc(&p.d_workspace, p.workspace_bytes), "cudaMalloc(bf workspace)");
+        if (single) detail::cuda_check(cudaStreamSynchronize(s.gpus[0].stream), "cudaStreamSynchronize");
+        const int rc = ggnn_b200_bf_query_u8(&p, static_cast<uint32_t>(query.N), nullptr);
+        cudaDeviceSynchronize();
+        cudaFree(p.d_workspace);
+        detail::abi_check(rc);
+        return s.return_results_on_gpu ? std::move(out) : to_host(std::move(out));
+      }
+    }
     if (single) {
       db = rows_f32(s.gpus[0], *single);
       detail::cuda_check(cudaStreamSynchronize(s.gpus[0].stream), "cudaStreamSynchronize");

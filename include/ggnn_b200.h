@@ -259,6 +259,26 @@ int ggnn_b200_interleave_rows(const float* d_src, float* d_dst, uint32_t N, uint
  * ---------------------------------------------------------------------------------------------- */
 int ggnn_b200_widen_u8(const uint8_t* d_src, float* d_dst, size_t count, ggnn_b200_stream_t stream);
 
+/* Brute-force query of uint8 vectors WITHOUT widening them: the same contract as ggnn_b200_bf_query (it replaces the
+ * BaseT = uint8_t instantiation of src/ggnn/query/bf_query_layer.cu:39-65), but d_base / d_query point to uint8 rows of D
+ * bytes and d_workspace (>= ggnn_b200_bf_query_u8_workspace_bytes()) is required.  The distances of uint8 vectors are
+ * integers below 2^24 for D <= 128, so  |b|^2 - 2 q.b + |q|^2  is evaluated EXACTLY on the int8 tensor cores
+ * (tcgen05.mma.kind::i8, u8 x u8 -> s32) and the K smallest (distance, index) pairs are bit-identical to the reference's
+ * fp32 arithmetic on the widened values.  Covered: Euclidean, D in {32, 64, 96, 128}, KQuery <= 128, N_base >= 128;
+ * _workspace_bytes returns 0 and the call GGNN_B200_ERR_UNSUPPORTED otherwise (widen the rows with ggnn_b200_widen_u8 and
+ * call ggnn_b200_bf_query: identical results). */
+size_t ggnn_b200_bf_query_u8_workspace_bytes(uint32_t D, int32_t measure, uint32_t KQuery, uint32_t N_base, uint32_t N_query);
+int ggnn_b200_bf_query_u8(const ggnn_b200_bf_query_params* p, uint32_t N_query, ggnn_b200_stream_t stream);
+
+/* Diagnostics of the path above (tools/bf_i8_check.py): _pack writes the tile-major, 128-byte-swizzled operand image of
+ * n_rows_pad (multiple of 128) rows -- 16 KB per 128-row tile, rows >= n_rows zero -- and the integer row norms;
+ * _mma multiplies ONE packed 128-row tile by another with `ksteps` (= D / 32) UMMA instructions and returns the
+ * 128 x 128 int32 products d_out[i][j] = sum_k a[i][k] * b[j][k]. */
+int ggnn_b200_debug_i8_pack(const uint8_t* d_rows, uint32_t n_rows, uint32_t n_rows_pad, uint32_t D, uint8_t* d_tiled,
+                            int32_t* d_norms, ggnn_b200_stream_t stream);
+int ggnn_b200_debug_i8_mma(const uint8_t* d_a_tile, const uint8_t* d_b_tile, uint32_t ksteps, int32_t* d_out,
+                           ggnn_b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

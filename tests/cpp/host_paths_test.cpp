@@ -145,6 +145,11 @@ int main(int argc, char** argv)
     size_t hits = 0;
     for (size_t i = 0; i < Nq8; ++i) hits += r_native.ids[i * K] == gt8.ids[i * K];
     check(hits > Nq8 / 2 && r_native.dists[0] == static_cast<float>(static_cast<int>(r_native.dists[0])), "uint8 base: integer distances, top-1 mostly exact");
+    // bfQuery on a uint8 base: int8 tensor-core contraction (rows never widened) == the widened fp32 path
+    setenv("GGNN_B200_NO_I8_BF", "1", 1);
+    const auto gt8_widened = n.bfQuery(query8, K);
+    unsetenv("GGNN_B200_NO_I8_BF");
+    check(same(gt8, gt8_widened), "uint8 base: bfQuery on the int8 tensor cores == bfQuery on widened rows");
   }
   std::printf("%s\n", failures ? "FAILED" : "ALL OK");
   return failures ? 1 : 0;

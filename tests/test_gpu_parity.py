@@ -147,6 +147,72 @@ def test_bf_query_tensor_core_path_candidate_overflow_falls_back_exactly(golden)
     assert np.array_equal(ids, g["bf_ids"]) and np.array_equal(dists, g["bf_dists"])  # == the reference's own output
 
 
+def c_bf_u8(base_u8, query_u8, K, measure=0):
+    """ggnn_b200_bf_query_u8: uint8 rows straight through the C ABI (int8 tensor cores, exact)"""
+    Nq, D = query_u8.shape
+    b, q = dev(base_u8), dev(query_u8)
+    ids = torch.full((Nq, K), -5, dtype=torch.int32, device="cuda")
+    dists = torch.full((Nq, K), -5.0, dtype=torch.float32, device="cuda")
+    p = _lib.BfQueryParams()
+    p.D, p.measure, p.KQuery, p.N_base = D, measure, K, base_u8.shape[0]
+    p.d_base, p.d_query, p.d_query_results, p.d_query_results_dists = b.data_ptr(), q.data_ptr(), ids.data_ptr(), dists.data_ptr()
+    nbytes = _lib.lib().ggnn_b200_bf_query_u8_workspace_bytes(D, measure, K, base_u8.shape[0], Nq)
+    assert nbytes > 0, "shape not covered by the uint8 tensor-core path"
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    p.d_workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+    _lib.check(_lib.lib().ggnn_b200_bf_query_u8(C.byref(p), Nq, stream()))
+    torch.cuda.synchronize()
+    return ids.cpu().numpy(), dists.cpu().numpy()
+
+
+@pytest.mark.parametrize("N,Nq,D,K,hi", [(3000, 70, 128, 10, 256), (1000, 300, 64, 32, 256), (2500, 129, 96, 1, 256),
+                                         (333, 5, 32, 10, 256), (40000, 257, 128, 10, 256), (20000, 200, 128, 100, 256),
+                                         (5000, 130, 96, 128, 4), (12345, 64, 64, 33, 2)])
+def test_bf_query_uint8_int8_tensor_core_path_bit_exact_vs_oracle(N, Nq, D, K, hi):
+    """uint8 vectors (BaseT = uint8_t, lib.h:26-28) as an exact integer contraction (tcgen05.mma.kind::i8) -> candidate
+    lists -> integer re-rank: same ids AND distances as the reference arithmetic on the widened values (oracle and the
+    exact fp32 SIMT scan), including ragged tile edges, duplicate rows and -- values below `hi` = 4 / 2 -- distance ties
+    by the hundred, which must come out in (distance, index) order (k_best_list.cuh:92,100)"""
+    rng = np.random.default_rng(N + D)
+    base = rng.integers(0, hi, (N, D), dtype=np.uint8)
+    query = rng.integers(0, hi, (Nq, D), dtype=np.uint8)
+    base[5] = base[3]
+    base[N - 1] = base[0]
+    query[0] = base[3]  # distance 0 twice
+    ids, dists = c_bf_u8(base, query, K)
+    bf, qf = base.astype(np.float32), query.astype(np.float32)
+    nq_o = min(Nq, 64 if K <= 32 else 16)
+    o_ids, o_d = O.bf_query(bf, qf[:nq_o], K, 0)
+    assert np.array_equal(ids[:nq_o], o_ids) and np.array_equal(dists[:nq_o], o_d)
+    e_ids, e_d = c_bf(bf, qf, K, 0)  # all queries vs the exact SIMT scan on the widened rows
+    assert np.array_equal(ids, e_ids) and np.array_equal(dists, e_d)
+
+
+def test_bf_query_uint8_candidate_overflow_and_unsupported_shapes():
+    """identical base rows: every row ties, the candidate lists overflow, the exact integer scan takes over; shapes the
+    path does not cover report UNSUPPORTED (the API then widens the rows: same results)"""
+    rng = np.random.default_rng(4)
+    base = np.tile(rng.integers(0, 256, (1, 64), dtype=np.uint8), (12000, 1))  # > the 8192-entry candidate capacity
+    base[::7, 0] ^= 1
+    query = rng.integers(0, 256, (40, 64), dtype=np.uint8)
+    ids, dists = c_bf_u8(base, query, 10)
+    e_ids, e_d = c_bf(base.astype(np.float32), query.astype(np.float32), 10, 0)
+    assert np.array_equal(ids, e_ids) and np.array_equal(dists, e_d)
+    l = _lib.lib()
+    assert l.ggnn_b200_bf_query_u8_workspace_bytes(100, 0, 10, 5000, 10) == 0   # D not a multiple of 32
+    assert l.ggnn_b200_bf_query_u8_workspace_bytes(128, 1, 10, 5000, 10) == 0   # cosine
+    assert l.ggnn_b200_bf_query_u8_workspace_bytes(128, 0, 129, 5000, 10) == 0  # K > 128
+    # ... and GGNN.bf_query gives the widened path's results for them (and for the covered shape, the int8 path's)
+    for D, K, measure in ((100, 10, 0), (128, 10, 1), (128, 200, 0), (128, 10, 0)):
+        b8 = rng.integers(0, 256, (3000, D), dtype=np.uint8)
+        q8 = rng.integers(0, 256, (20, D), dtype=np.uint8)
+        g = ggnn.GGNN()
+        g.set_base(torch.from_numpy(b8))
+        gi, gd = g.bf_query(torch.from_numpy(q8), K, ggnn.DistanceMeasure(measure))
+        o_ids, o_d = O.bf_query(b8.astype(np.float32), q8.astype(np.float32), K, measure)
+        assert np.array_equal(gi.numpy(), o_ids) and np.array_equal(gd.numpy(), o_d)
+
+
 # ------------------------------------------------------------------------------------------------
 # ANN query
 # ------------------------------------------------------------------------------------------------
