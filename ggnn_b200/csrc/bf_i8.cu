@@ -231,12 +231,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
     // has seen, tightened by what the other lists of the same query have published in tau_g
     int tau = I8_INF;
     uint32_t c_pos = 0, c_left = 0;  // this thread's current chunk of candidate slots
+    // the per-tile global loads (base norm of this thread's row, shared bound) are issued one tile ahead: their latency
+    // stays off the tile loop's critical path (a bound that is one tile old is still a bound)
+    int bn_next = (ch == 0 && n_tiles > 0 && n_begin + r < n_end) ? a.bnorm[n_begin + r] : 0x7fffffff;
+    int tg_next = (live && n_tiles > 0) ? static_cast<int>(__ldcg(&a.tau_g[q])) : I8_INF;
     for (uint32_t t = 0; t < n_tiles; ++t) {
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
       const uint32_t n0 = n_begin + t * I8_BN;
       // stage the tile's base norms (rows past the end: zero rows of the packed operand, rejected again in pass 2)
-      if (ch == 0) s_bnorm[acc * I8_BN + r] = (n0 + r < n_end) ? a.bnorm[n0 + r] : 0x7fffffff;
-      if (live) tau = min(tau, static_cast<int>(__ldcg(&a.tau_g[q])));
+      if (ch == 0) s_bnorm[acc * I8_BN + r] = bn_next;
+      tau = min(tau, tg_next);
+      if (t + 1 < n_tiles) {
+        if (ch == 0) bn_next = (n0 + I8_BN + r < n_end) ? a.bnorm[n0 + I8_BN + r] : 0x7fffffff;
+        if (live) tg_next = static_cast<int>(__ldcg(&a.tau_g[q]));
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
@@ -277,14 +285,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
           if (n0 + col + u >= n_end) continue;
           const int s = bn_u - 2 * acc_u + qn;  // exact squared distance
           if (s <= tau) {                       // ties with the K-th best stay candidates: the final order is (dist, id)
-            // candidate slots are handed out in chunks of TC_CHUNK per (query, list): one returning atomic per chunk
-            if (c_left == 0) {
-              c_pos = atomicAdd(&a.cnt[q], 8u);
-              c_left = 8u;
+            if (a.cand != nullptr) {            // (nullptr: the sample pass only establishes the bounds)
+              // candidate slots are handed out in chunks of 8 per (query, list): one returning atomic per chunk
+              if (c_left == 0) {
+                c_pos = atomicAdd(&a.cnt[q], 8u);
+                c_left = 8u;
+              }
+              if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + col + u);
+              ++c_pos;
+              --c_left;
             }
-            if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + col + u);
-            ++c_pos;
-            --c_left;
             if (s < tau) {
               // the row's K best distances so far form a MAX-HEAP in kb[0..K): replace its root by s and sift down
               uint32_t i = 0;
@@ -579,6 +589,19 @@ static int i8_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const I8Works
   auto gemm = i8_gemm_kernel<KP, NSTAGE>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(i8_gemm_kernel)");
+  // Sample pass: every list of the main pass starts without a bound and makes its first tile's rows candidates one by
+  // one.  One split over a prefix of the base (no candidates, no published lists) leaves in tau_g the K-th best of about
+  // 1/16 of the rows; the main pass then starts with that bound and only handles the rows below it.
+  if (splits > 1 && env_u32("GGNN_B200_BF_PRESAMPLE", 1)) {
+    const uint32_t sample_tiles = std::min(tiles_per_split, std::max(8u, n_tiles / 16));
+    I8GemmArgs sa = ga;
+    sa.N_base = std::min(N, sample_tiles * I8_BN);
+    sa.rows_per_split = sample_tiles * I8_BN;
+    sa.cand = nullptr;
+    sa.pub = nullptr;
+    gemm<<<dim3(q_tiles, 1), I8_THREADS, smem, stream>>>(sa);
+    if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "i8_gemm_kernel launch (sample pass)");
+  }
   gemm<<<dim3(q_tiles, splits), I8_THREADS, smem, stream>>>(ga);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "i8_gemm_kernel launch");
 

@@ -170,18 +170,43 @@ def stage_time():
         base, query = gen(1_000_000, 10_000, 128, "manifold", 3)
         i1, d1, t1 = run_bf(base, query, K, True)
         i0, d0, t0 = run_bf(base, query, K, False)
-        same = bool(torch.equal(i0, i1) and torch.equal(d0, d1))
+        os.environ["GGNN_B200_BF_PRESAMPLE"] = "0"  # without the sample pass that presets the bounds
+        i1n, d1n, t1n = run_bf(base, query, K, True)
+        i0n, d0n, t0n = run_bf(base, query, K, False)
+        os.environ.pop("GGNN_B200_BF_PRESAMPLE")
+        same = bool(torch.equal(i0, i1) and torch.equal(d0, d1) and torch.equal(i1n, i1) and torch.equal(d1n, d1) and
+                    torch.equal(i0n, i1) and torch.equal(d0n, d1))
         print(f"[time] 1M x 128 uint8, 10 000 queries, K={K}: identical={same} | int8 tensor path {t1:.2f} ms "
-              f"({2 * 1e6 * 1e4 * 128 / t1 / 1e9:.0f} useful Tops/s) | widened 3xTF32 path {t0:.2f} ms", flush=True)
+              f"({2 * 1e6 * 1e4 * 128 / t1 / 1e9:.0f} useful Tops/s; {t1n:.2f} ms without the sample pass) | "
+              f"widened 3xTF32 path {t0:.2f} ms ({t0n:.2f} ms without the sample pass)", flush=True)
         ok = ok and same
     return ok
+
+
+def stage_profile():
+    """one call per path and K at the 1M shape, for a kernel launch list:
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file <csv> python tools/bf_i8_check.py 5"""
+    base, query = gen(1_000_000, 10_000, 128, "manifold", 3)
+    os.environ["GGNN_B200_BF_DEBUG"] = "1"  # candidate statistics on stderr
+    for native in (True, False):
+        if not native:
+            os.environ["GGNN_B200_NO_I8_BF"] = "1"
+        g = ggnn.GGNN()
+        g.set_return_results_on_gpu(True)
+        g.set_base(base)
+        for K in (10, 100):
+            g.bf_query(query, K)
+            torch.cuda.synchronize()
+    os.environ.pop("GGNN_B200_NO_I8_BF", None)
+    os.environ.pop("GGNN_B200_BF_DEBUG", None)
+    return True
 
 
 def main():
     stages = sys.argv[1] if len(sys.argv) > 1 else "1234"
     t0 = time.time()
     res = {}
-    for key, fn in (("1", stage_pack), ("2", stage_mma), ("3", stage_e2e), ("4", stage_time)):
+    for key, fn in (("1", stage_pack), ("2", stage_mma), ("3", stage_e2e), ("4", stage_time), ("5", stage_profile)):
         if key in stages:
             try:
                 res[fn.__name__] = fn()
