@@ -68,6 +68,7 @@ struct I8GemmArgs {
   uint32_t N_base, N_query, K, cap;
   uint32_t rows_per_split;  // multiple of I8_BN
   uint32_t ksteps;          // D / 32: UMMA_K = 32 bytes
+  uint32_t rotate;          // CTA x starts its walk over the split's tiles at tile (x * rotate) % n_tiles (0: all at tile 0)
   unsigned int* pub;        // [N_query][2 * splits][K] published best lists (merger warp), or nullptr
   const int32_t* bnorm;     // [N_base]
   const int32_t* qnorm;     // [N_query]
@@ -108,6 +109,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
   const uint32_t n_begin = blockIdx.y * a.rows_per_split;
   const uint32_t n_end = min(a.N_base, n_begin + a.rows_per_split);
   const uint32_t n_tiles = (n_end > n_begin) ? (n_end - n_begin + I8_BN - 1) / I8_BN : 0;
+  // The CTAs of a split all stream the same base tiles.  Started together they would ask for the same 16 KB record at
+  // the same time, over and over, and queue up on the few L2 slices that hold it; so every CTA walks the split's tiles
+  // in the same cyclic order but from its own starting tile.
+  const uint32_t rot = n_tiles > 1 ? (blockIdx.x * a.rotate) % n_tiles : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -139,8 +144,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
       mbar_expect_tx(a_full, I8_TILE_BYTES);
       bulk_g2s(sA, a.q_tiled + static_cast<size_t>(blockIdx.x) * I8_TILE_BYTES, I8_TILE_BYTES, a_full);
       uint32_t stage = 0, phase = 0;
+      uint32_t ti = rot;
       for (uint32_t t = 0; t < n_tiles; ++t) {
-        const size_t tile = (n_begin / I8_BN) + t;
+        const size_t tile = (n_begin / I8_BN) + ti;
+        if (++ti == n_tiles) ti = 0;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], I8_TILE_BYTES);
         bulk_g2s(sB + stage * I8_TILE_BYTES, a.b_tiled + tile * I8_TILE_BYTES, I8_TILE_BYTES, &full[stage]);
@@ -233,16 +240,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
     uint32_t c_pos = 0, c_left = 0;  // this thread's current chunk of candidate slots
     // the per-tile global loads (base norm of this thread's row, shared bound) are issued one tile ahead: their latency
     // stays off the tile loop's critical path (a bound that is one tile old is still a bound)
-    int bn_next = (ch == 0 && n_tiles > 0 && n_begin + r < n_end) ? a.bnorm[n_begin + r] : 0x7fffffff;
+    uint32_t ti = rot;  // position of the current tile in the split (same cyclic order as the producer's)
+    int bn_next = (ch == 0 && n_tiles > 0 && n_begin + ti * I8_BN + r < n_end) ? a.bnorm[n_begin + ti * I8_BN + r] : 0x7fffffff;
     int tg_next = (live && n_tiles > 0) ? static_cast<int>(__ldcg(&a.tau_g[q])) : I8_INF;
     for (uint32_t t = 0; t < n_tiles; ++t) {
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
-      const uint32_t n0 = n_begin + t * I8_BN;
+      const uint32_t n0 = n_begin + ti * I8_BN;
+      if (++ti == n_tiles) ti = 0;
       // stage the tile's base norms (rows past the end: zero rows of the packed operand, rejected again in pass 2)
       if (ch == 0) s_bnorm[acc * I8_BN + r] = bn_next;
       tau = min(tau, tg_next);
       if (t + 1 < n_tiles) {
-        if (ch == 0) bn_next = (n0 + I8_BN + r < n_end) ? a.bnorm[n0 + I8_BN + r] : 0x7fffffff;
+        const uint32_t n1 = n_begin + ti * I8_BN;  // first row of the next tile
+        if (ch == 0) bn_next = (n1 + r < n_end) ? a.bnorm[n1 + r] : 0x7fffffff;
         if (live) tg_next = static_cast<int>(__ldcg(&a.tau_g[q]));
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -285,16 +295,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
           if (n0 + col + u >= n_end) continue;
           const int s = bn_u - 2 * acc_u + qn;  // exact squared distance
           if (s <= tau) {                       // ties with the K-th best stay candidates: the final order is (dist, id)
-            if (a.cand != nullptr) {            // (nullptr: the sample pass only establishes the bounds)
-              // candidate slots are handed out in chunks of 8 per (query, list): one returning atomic per chunk
-              if (c_left == 0) {
-                c_pos = atomicAdd(&a.cnt[q], 8u);
-                c_left = 8u;
-              }
-              if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + col + u);
-              ++c_pos;
-              --c_left;
+            // candidate slots are handed out in chunks of 8 per (query, list): one returning atomic per chunk
+            if (c_left == 0) {
+              c_pos = atomicAdd(&a.cnt[q], 8u);
+              c_left = 8u;
             }
+            if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + col + u);
+            ++c_pos;
+            --c_left;
             if (s < tau) {
               // the row's K best distances so far form a MAX-HEAP in kb[0..K): replace its root by s and sift down
               uint32_t i = 0;
@@ -575,6 +583,8 @@ static int i8_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const I8Works
   ga.cap = cap;
   ga.rows_per_split = tiles_per_split * I8_BN;
   ga.ksteps = D / 32;
+  // starting tiles spread evenly over the split (GGNN_B200_BF_I8_ROTATE=0: every CTA starts at the split's first tile)
+  ga.rotate = env_u32("GGNN_B200_BF_I8_ROTATE", 1) ? std::max(1u, tiles_per_split / std::max(1u, q_tiles)) : 0u;
   ga.bnorm = w.bnorm;
   ga.qnorm = w.qnorm;
   ga.q_tiled = w.q_tiled;
@@ -589,19 +599,6 @@ static int i8_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const I8Works
   auto gemm = i8_gemm_kernel<KP, NSTAGE>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(i8_gemm_kernel)");
-  // Sample pass: every list of the main pass starts without a bound and makes its first tile's rows candidates one by
-  // one.  One split over a prefix of the base (no candidates, no published lists) leaves in tau_g the K-th best of about
-  // 1/16 of the rows; the main pass then starts with that bound and only handles the rows below it.
-  if (splits > 1 && env_u32("GGNN_B200_BF_PRESAMPLE", 1)) {
-    const uint32_t sample_tiles = std::min(tiles_per_split, std::max(8u, n_tiles / 16));
-    I8GemmArgs sa = ga;
-    sa.N_base = std::min(N, sample_tiles * I8_BN);
-    sa.rows_per_split = sample_tiles * I8_BN;
-    sa.cand = nullptr;
-    sa.pub = nullptr;
-    gemm<<<dim3(q_tiles, 1), I8_THREADS, smem, stream>>>(sa);
-    if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "i8_gemm_kernel launch (sample pass)");
-  }
   gemm<<<dim3(q_tiles, splits), I8_THREADS, smem, stream>>>(ga);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "i8_gemm_kernel launch");
 

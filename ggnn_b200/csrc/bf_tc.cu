@@ -374,16 +374,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
           const float bn_u = u == 0 ? bn.x : (u == 1 ? bn.y : (u == 2 ? bn.z : bn.w));
           const float s = fmaxf(acc_u + bn_u + qn, 0.f);
           if (s < tau + margin) {
-            if (a.cand != nullptr) {  // (nullptr: the sample pass only establishes the bounds)
-              // candidate slots are handed out in chunks of TC_CHUNK per (query, list): one returning atomic per chunk
-              if (c_left == 0) {
-                c_pos = atomicAdd(&a.cnt[q], TC_CHUNK);
-                c_left = TC_CHUNK;
-              }
-              if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + col + u);
-              ++c_pos;
-              --c_left;
+            // candidate slots are handed out in chunks of TC_CHUNK per (query, list): one returning atomic per chunk
+            if (c_left == 0) {
+              c_pos = atomicAdd(&a.cnt[q], TC_CHUNK);
+              c_left = TC_CHUNK;
             }
+            if (c_pos < a.cap) a.cand[static_cast<size_t>(q) * a.cap + c_pos] = static_cast<int32_t>(n0 + col + u);
+            ++c_pos;
+            --c_left;
             if (s < tau) {
               // the row's K best scores so far form a MAX-HEAP in kb[0..K): replace its root (the K-th best, which
               // bounds tau) by s and sift down -- O(log K) instead of the O(K) shifts of a sorted list (K = 100: the
@@ -659,20 +657,6 @@ static int tc_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const TcWorks
   auto gemm = tc_gemm_kernel<KB, KP, NSTAGE>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
-  // Sample pass (opt-out GGNN_B200_BF_PRESAMPLE=0): every list of the main pass starts without a bound and makes its first
-  // tile's rows candidates one by one.  One split over a prefix of the base (no candidates, no published lists) leaves in
-  // tau_g the K-th best score of about 1/16 of the rows -- an upper bound of the final K-th best like any other -- and
-  // the main pass starts from it.
-  if (splits > 1 && env_u32("GGNN_B200_BF_PRESAMPLE", 1)) {
-    const uint32_t sample_tiles = std::min(tiles_per_split, std::max(8u, n_tiles / 16));
-    TcGemmArgs sa = ga;
-    sa.N_base = std::min(N, sample_tiles * TC_BN);
-    sa.rows_per_split = sample_tiles * TC_BN;
-    sa.cand = nullptr;
-    sa.pub = nullptr;
-    gemm<<<dim3(q_tiles, 1), TC_THREADS, smem, stream>>>(sa);
-    if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_gemm_kernel launch (sample pass)");
-  }
   gemm<<<dim3(q_tiles, splits), TC_THREADS, smem, stream>>>(ga);
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error(e, "tc_gemm_kernel launch");
 
