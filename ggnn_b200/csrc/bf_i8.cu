@@ -39,6 +39,7 @@ constexpr uint32_t I8_TILE_BYTES = I8_BN * I8_ROW_BYTES;  // 16 KB
 constexpr int I8_THREADS = 384;           // warps 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 merger, 4..11 epilogue
 constexpr int I8_INF = 0x7f7f7f7f;        // "no bound yet" (what cudaMemset(0x7f) writes); every real score is < 2^25
 constexpr int I8_KP_MAX = 128;
+constexpr int I8_BNORM_INTS = 8 * 2 * 64;  // base norms of a tile, staged per epilogue warp (its 64 columns, two tiles)
 
 // ---- stage 1: pack ------------------------------------------------------------------------------
 // one thread per 16-byte chunk, 8 chunks per output row; rows >= n_rows (up to n_rows_pad) and chunks past D are zero
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
   unsigned char* sA = smem;                                                  // 16 KB query tile
   unsigned char* sB = smem + I8_TILE_BYTES;                                  // [NSTAGE] 16 KB base tiles
   int* s_kbest = reinterpret_cast<int*>(sB + NSTAGE * I8_TILE_BYTES);        // [2 column halves][128][KP]
-  int* s_bnorm = s_kbest + 2 * I8_BM * KP;                                   // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bnorm + 2 * I8_BN);
+  int* s_bnorm = s_kbest + 2 * I8_BM * KP;                                   // [8 epilogue warps][2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bnorm + I8_BNORM_INTS);
   uint64_t* full = bars;                    // [NSTAGE]
   uint64_t* empty = bars + NSTAGE;          // [NSTAGE]
   uint64_t* a_full = bars + 2 * NSTAGE;     // [1]
@@ -238,45 +239,51 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
     // has seen, tightened by what the other lists of the same query have published in tau_g
     int tau = I8_INF;
     uint32_t c_pos = 0, c_left = 0;  // this thread's current chunk of candidate slots
-    // the per-tile global loads (base norm of this thread's row, shared bound) are issued one tile ahead: their latency
-    // stays off the tile loop's critical path (a bound that is one tile old is still a bound)
+    // the per-tile global loads (base norms, shared bound) are issued one tile ahead: their latency stays off the tile
+    // loop's critical path (a bound that is one tile old is still a bound)
     uint32_t ti = rot;  // position of the current tile in the split (same cyclic order as the producer's)
-    int bn_next = (ch == 0 && n_tiles > 0 && n_begin + ti * I8_BN + r < n_end) ? a.bnorm[n_begin + ti * I8_BN + r] : 0x7fffffff;
+    // The norms of the tile's base rows are staged PER WARP (its 64 columns: lane l loads columns l and 32 + l), so the
+    // eight epilogue warps never wait for each other: a warp that has candidates to file falls behind by up to the two
+    // accumulator buffers and catches up again, instead of stalling the other seven at a CTA-wide barrier every tile.
+    int* s_bn_w = s_bnorm + (warp - 4) * 128;
+    auto load_bn = [&](uint32_t row) { return row < n_end ? a.bnorm[row] : 0x7fffffff; };
+    const uint32_t c0 = 64u * ch + lane;  // this lane's first column
+    int bn_next0 = n_tiles > 0 ? load_bn(n_begin + ti * I8_BN + c0) : 0;
+    int bn_next1 = n_tiles > 0 ? load_bn(n_begin + ti * I8_BN + c0 + 32u) : 0;
     int tg_next = (live && n_tiles > 0) ? static_cast<int>(__ldcg(&a.tau_g[q])) : I8_INF;
     for (uint32_t t = 0; t < n_tiles; ++t) {
       const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
       const uint32_t n0 = n_begin + ti * I8_BN;
       if (++ti == n_tiles) ti = 0;
-      // stage the tile's base norms (rows past the end: zero rows of the packed operand, rejected again in pass 2)
-      if (ch == 0) s_bnorm[acc * I8_BN + r] = bn_next;
+      // (rows past the end: zero rows of the packed operand, rejected again in pass 2)
+      int* bnw = s_bn_w + acc * 64;
+      bnw[lane] = bn_next0;
+      bnw[32 + lane] = bn_next1;
       tau = min(tau, tg_next);
       if (t + 1 < n_tiles) {
         const uint32_t n1 = n_begin + ti * I8_BN;  // first row of the next tile
-        if (ch == 0) bn_next = (n1 + r < n_end) ? a.bnorm[n1 + r] : 0x7fffffff;
+        bn_next0 = load_bn(n1 + c0);
+        bn_next1 = load_bn(n1 + c0 + 32u);
         if (live) tg_next = static_cast<int>(__ldcg(&a.tau_g[q]));
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      __syncwarp();
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
-      const int4* bn4 = reinterpret_cast<const int4*>(s_bnorm + acc * I8_BN);
+      const int4* bn4 = reinterpret_cast<const int4*>(bnw);  // [16 groups of 4 columns]
       bool improved = false;
       // pass 1, branch-free: which groups of 4 columns hold a row with |b|^2 - 2 acc <= tau - |q|^2 ?
       const int thr = tau - qn;
       uint32_t m = 0;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * ch + cc;
-        int v[32];
-        tmem_ld32i(tmem_base + acc * I8_BN + c * 32 + ((ew * 32u) << 16), v);
-        uint32_t mc = 0;
+      {
+        int v[64];
+        tmem_ld64i(tmem_base + acc * I8_BN + 64u * ch + ((ew * 32u) << 16), v);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int4 bn = bn4[c * 8 + j4];
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const int4 bn = bn4[j4];
           const int s0 = bn.x - 2 * v[4 * j4 + 0], s1 = bn.y - 2 * v[4 * j4 + 1];
           const int s2 = bn.z - 2 * v[4 * j4 + 2], s3 = bn.w - 2 * v[4 * j4 + 3];
-          mc |= (min(min(s0, s1), min(s2, s3)) <= thr ? 1u : 0u) << j4;
+          m |= (min(min(s0, s1), min(s2, s3)) <= thr ? 1u : 0u) << j4;
         }
-        m |= mc << (8 * cc);
       }
       if (!live) m = 0;  // rows past the last query
       // pass 2, rare once tau is tight: the warp walks the union of the lanes' group masks; the 4 columns of a group
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_gemm_kernel(const I8GemmArgs
         int w[4];
         tmem_ld4i(tmem_base + acc * I8_BN + col + ((ew * 32u) << 16), w);
         if (!((m >> g) & 1u)) continue;
-        const int4 bn = bn4[col >> 2];
+        const int4 bn = bn4[g];
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           const int acc_u = u == 0 ? w[0] : (u == 1 ? w[1] : (u == 2 ? w[2] : w[3]));
@@ -595,7 +602,7 @@ static int i8_run(const ggnn_b200_bf_query_params& p, uint32_t Nq, const I8Works
   ga.pub = env_u32("GGNN_B200_BF_MERGER", 1) ? w.pub : nullptr;
   if (ga.pub && (e = cudaMemsetAsync(w.pub, 0x7f, static_cast<size_t>(Nq) * 2 * splits * p.KQuery * 4, stream)) != cudaSuccess)
     return set_cuda_error(e, "memset pub");
-  const size_t smem = static_cast<size_t>(1 + NSTAGE) * I8_TILE_BYTES + 2 * I8_BM * KP * 4 + 2 * I8_BN * 4 + 256 + 1024;
+  const size_t smem = static_cast<size_t>(1 + NSTAGE) * I8_TILE_BYTES + 2 * I8_BM * KP * 4 + I8_BNORM_INTS * 4 + 256 + 1024;
   auto gemm = i8_gemm_kernel<KP, NSTAGE>;
   if ((e = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return set_cuda_error(e, "cudaFuncSetAttribute(i8_gemm_kernel)");
