@@ -117,3 +117,48 @@ def test_oracle_eval_matches_definition():
     e = O.evaluate(gt, res, 10)
     assert e["cK"] == pytest.approx((50 * 5 - 25) / 500)
     assert e["c1"] == pytest.approx(0.5) and e["rK"] == pytest.approx(0.5)
+
+
+@pytest.mark.parametrize("D,hi", [(128, 256), (96, 256), (64, 4), (32, 2)])
+def test_uint8_distances_are_exact_integers_in_the_reference_arithmetic(D, hi):
+    """The premise of the uint8 kernels (csrc/query.cu fetch_u8, csrc/bf_i8.cu): the reference computes on
+    static_cast<float>(value) (include/ggnn/cuda_utils/distance.cuh:104-139) and for D <= 128 every partial sum is an
+    integer below 2^24, so its fp32 result IS the integer |b|^2 - 2 q.b + |q|^2 -- and the K best by (distance, index)
+    (k_best_list.cuh:92,100) are what an integer brute force returns.  Checked on the oracle, ties by the hundred included."""
+    rng = np.random.default_rng(D + hi)
+    base = rng.integers(0, hi, (3000, D), dtype=np.uint8)
+    query = rng.integers(0, hi, (40, D), dtype=np.uint8)
+    base[5] = base[3]
+    base[100] = 255 if hi == 256 else hi - 1   # the largest norm
+    query[0] = base[3]
+    K = 32
+    o_ids, o_d = O.bf_query(base.astype(np.float32), query.astype(np.float32), K, 0)
+    b, q = base.astype(np.int64), query.astype(np.int64)
+    d = (b * b).sum(1)[None, :] - 2 * (q @ b.T) + (q * q).sum(1)[:, None]
+    assert d.max() < 2 ** 24
+    key = d * (1 << 32) + np.arange(base.shape[0])[None, :]
+    top = np.sort(key, axis=1)[:, :K]
+    assert np.array_equal(o_ids, (top & 0xffffffff).astype(np.int32))
+    assert np.array_equal(o_d, (top >> 32).astype(np.float32))
+
+
+def test_bf_i8_check_layout_model_matches_a_byte_by_byte_loop():
+    """tools/bf_i8_check.py checks the operand packing of csrc/bf_i8.cu against pack_model(); pack_model() itself is
+    checked here against the definition: byte b of 16-byte chunk c of row r of tile t at t * 16 KB + r * 128 + ((c ^ (r & 7)) << 4) + b
+    (the SWIZZLE_128B image of a K-major UMMA operand), rows past the end and bytes past D zero."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "bf_i8_check", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bf_i8_check.py"))
+    T = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(T)
+    rng = np.random.default_rng(0)
+    for n, n_pad, D in ((300, 384, 96), (128, 128, 128), (5, 128, 32)):
+        rows = rng.integers(0, 256, (n, D), dtype=np.uint8)
+        want = np.zeros(n_pad * 128, dtype=np.uint8)
+        for row in range(n):
+            t, r = row >> 7, row & 127
+            for c in range(D // 16):
+                off = t * 16384 + r * 128 + ((c ^ (r & 7)) << 4)
+                want[off:off + 16] = rows[row, c * 16:(c + 1) * 16]
+        assert np.array_equal(T.pack_model(rows, n_pad), want)

@@ -15,6 +15,7 @@ timeout 900 python bench.py > $O/r${R}_bench_ours.json 2> $O/r${R}_bench_ours.er
 if [ -z "$quick" ]; then
   timeout 600 python bench.py --impl reference > $O/r${R}_bench_reference.json 2> $O/r${R}_bench_reference.err; echo "reference rc=$?"; cut -c1-200 $O/r${R}_bench_reference.json
 fi
+timeout 120 python tools/bf_i8_check.py > $O/r${R}_bf_i8_check.log 2>&1; echo "bf_i8_check rc=$?"; tail -3 $O/r${R}_bf_i8_check.log
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r${R}_launches_bench.csv \
   python bench.py --steps 2 --warmup 3 --batches-per-step 4 --no-config4 --no-extras > $O/r${R}_ncu_list.log 2>&1; echo "launch list rc=$?"
 if [ -z "$quick" ]; then
@@ -22,6 +23,8 @@ if [ -z "$quick" ]; then
     python bench.py --steps 2 --warmup 3 --batches-per-step 4 --streams 1 --e2e-depth 1 --no-config4 --no-extras > $O/r${R}_ncu_full.log 2>&1; echo "full capture rc=$?"
   timeout 300 ncu --set full --clock-control none -k regex:tc_gemm_kernel -s 7 -c 1 -f -o $O/r${R}_bf_tc_gemm \
     python tools/bf_tc_check.py > $O/r${R}_ncu_bf.log 2>&1; echo "bf capture rc=$?"
+  timeout 200 ncu --set full --clock-control none --import-source on -k regex:i8_gemm_kernel -c 1 -f -o $O/r${R}_bf_i8_gemm \
+    python tools/bf_i8_check.py 5 > $O/r${R}_ncu_bf_i8.log 2>&1; echo "bf_i8 capture rc=$?"
   timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv \
     --log-file $O/r${R}_launches_build.csv python tools/build_profile.py > $O/r${R}_ncu_build.log 2>&1; echo "build list rc=$?"
 fi
