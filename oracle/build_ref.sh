@@ -31,6 +31,12 @@ if [ -f "$HERE/ref_driver.cpp" ]; then
   "$NVCC" "${FLAGS[@]}" -x cu "$HERE/ref_driver.cpp" -o "$OUT/ref_driver" \
       -L"$OUT" -lggnn_ref -lcurand -Xlinker -rpath -Xlinker '$ORIGIN'
 fi
+# Host-only driver of the reference's ResultMerger / Evaluator (no GPU needed): tools/gen_host_golden.py runs it to make
+# tests/golden/host_merge_eval.npz.  Plain g++: the program defines cudaPeekAtLastError itself (see its header comment).
+if [ -f "$HERE/ref_host_check.cpp" ]; then
+  g++ -std=c++20 -O2 -I"$REF/include" -I"$HERE/ref_shim" -I/usr/local/cuda/include "$HERE/ref_host_check.cpp" \
+      -o "$OUT/ref_host_check" -rdynamic -L"$OUT" -lggnn_ref -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$ORIGIN'
+fi
 # The hybrid (compiled): the same unmodified reference objects, except that its two thin
 # host -> CUDA launcher files (query_kernels.cu, graph_construction.cu) are replaced by
 # integration/reference_launchers/*.cu, which call libggnn_b200.so through the C ABI.

@@ -162,3 +162,52 @@ def test_bf_i8_check_layout_model_matches_a_byte_by_byte_loop():
                 off = t * 16384 + r * 128 + ((c ^ (r & 7)) << 4)
                 want[off:off + 16] = rows[row, c * 16:(c + 1) * 16]
         assert np.array_equal(T.pack_model(rows, n_pad), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side result handling: oracle restatements and the product's Evaluator against outputs of the UNMODIFIED reference
+# (tests/golden/host_merge_eval.npz, produced by tools/gen_host_golden.py + oracle/ref_host_check.cpp; no GPU involved)
+# ------------------------------------------------------------------------------------------------
+def _host_golden():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_host_golden", os.path.join(root, "tools", "gen_host_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    return G, np.load(os.path.join(root, "tests", "golden", "host_merge_eval.npz"))
+
+
+def test_oracle_result_merge_matches_reference_result_merger():
+    """orc_merge_results == ggnn::ResultMerger::merge (src/ggnn/base/result_merger.cpp:51-149) on per-GPU sorted lists with
+    distinct distances: ids (with the reference's partition * spg * N_shard offset) and distances, for several GPUs x shards
+    per GPU, and the single-GPU copy-through of the first KQuery entries"""
+    G, z = _host_golden()
+    assert [tuple(c) for c in z["merge_cases"]] == G.MERGE_CASES
+    for i, case in enumerate(G.MERGE_CASES):
+        num_gpus, spg, Nq, K, N_shard = case
+        ids, d = G.merge_inputs(case, 100 + i)
+        o_ids, o_d = O.merge_results(ids, d, K, spg * N_shard)
+        assert np.array_equal(o_ids, z[f"merge{i}_ids"]), case
+        assert np.array_equal(o_d, z[f"merge{i}_dists"]), case
+
+
+def test_oracle_and_product_evaluator_match_reference_evaluator():
+    """orc_eval and ggnn_b200.Evaluator == ggnn::Evaluator (src/ggnn/base/eval.cpp:88-242): c@1, c@K, r@K and their
+    duplicate-aware variants on float and uint8 data, Euclidean and cosine (incl. the b_norm quirk of eval.cpp:52), bases
+    with duplicate rows, K_gt < KQuery and KQuery = 1"""
+    import torch
+    import ggnn_b200 as ggnn
+    G, z = _host_golden()
+    assert [tuple(c) for c in z["eval_cases"]] == G.EVAL_CASES
+    for i, case in enumerate(G.EVAL_CASES):
+        N, Nq, D, Kgt, K, measure, is_u8 = case
+        base, query, gt, res = G.eval_inputs(case, 200 + i)
+        want = z[f"eval{i}_values"]
+        o = O.evaluate(gt, res, K, base, query, measure)
+        got = np.array([o[k] for k in ("c1", "c1_dup", "cK", "cK_dup", "rK", "rK_dup")], np.float32)
+        assert np.array_equal(got, want), (case, got, want)
+        e = ggnn.Evaluator(torch.from_numpy(base), torch.from_numpy(query), torch.from_numpy(gt), K,
+                           ggnn.DistanceMeasure(measure)).evaluate_results(torch.from_numpy(res))
+        mine = np.array([e.c1, e.c1_dup, e.c_k_query, e.c_k_query_dup, e.r_k_query, e.r_k_query_dup], np.float64)
+        assert np.allclose(mine, want.astype(np.float64), rtol=0, atol=1e-6), (case, mine, want)
