@@ -12,6 +12,9 @@
 //     in : u32 N, N_query, D, K_gt, KQuery, measure, is_uint8; base[N][D], query[N_query][D] (float or uint8);
 //          int32 gt[N_query][K_gt]; int32 results[N_query][KQuery]
 //     out: float c1, c1_dup, cK, cK_dup, rK, rK_dup; u32 top1DuplicateEnd[N_query]; u32 topKDuplicateEnd[N_query]
+//   ref_host_check store <in.bin> <file>   /   ref_host_check load <file> <from> <num> <out.bin>
+//     Dataset<T>::store and GenericDataset::load (src/ggnn/base/dataset.cu:118-226): the fvecs / bvecs / ivecs files
+//     of SURVEY 8(f) rank 3
 #include <ggnn/base/dataset.cuh>
 #include <ggnn/base/eval.h>
 #include <ggnn/base/result_merger.h>
@@ -115,15 +118,45 @@ static int run_eval(const char* in, const char* out)
   return 0;
 }
 
+// store: in = u32 type (0 float, 1 uint8, 2 int32), N, D; data[N][D]  ->  Dataset<T>::store(<out file>)   (dataset.cu:215-226)
+static int run_store(const char* in, const char* out)
+{
+  const auto buf = slurp(in);
+  Reader r{buf.data(), buf.data() + buf.size()};
+  const uint32_t type = r.u32(), N = r.u32(), D = r.u32();
+  const size_t n = static_cast<size_t>(N) * D;
+  if (type == 0) ggnn::Dataset<float>::copy({r.take<float>(n), n}, D).store(out);
+  else if (type == 1) ggnn::Dataset<uint8_t>::copy({r.take<uint8_t>(n), n}, D).store(out);
+  else ggnn::Dataset<int32_t>::copy({r.take<int32_t>(n), n}, D).store(out);
+  return 0;
+}
+
+// load: GenericDataset::load(<in file>.fvecs|.bvecs|.ivecs, from, num)  ->  out = u32 N, D, bytes per element; data
+// (dataset.cu:118-213)
+static int run_load(const char* in, uint32_t from, uint32_t num, const char* out)
+{
+  const ggnn::GenericDataset d = ggnn::GenericDataset::load(in, from, num);
+  const uint32_t hdr[3] = {static_cast<uint32_t>(d.N), d.D, static_cast<uint32_t>(d.element_size())};
+  FILE* f = std::fopen(out, "wb");
+  if (!f) { std::perror(out); return 2; }
+  std::fwrite(hdr, sizeof(uint32_t), 3, f);
+  std::fwrite(d.reinterpret<unsigned char>().data(), 1, d.required_size_bytes(), f);
+  std::fclose(f);
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
+  if (argc == 6 && std::string(argv[1]) == "load")
+    return run_load(argv[2], static_cast<uint32_t>(std::stoul(argv[3])), static_cast<uint32_t>(std::stoul(argv[4])), argv[5]);
   if (argc != 4) {
-    std::fprintf(stderr, "usage: %s merge|eval <in.bin> <out.bin>\n", argv[0]);
+    std::fprintf(stderr, "usage: %s merge|eval|store <in.bin> <out>  |  load <file> <from> <num> <out.bin>\n", argv[0]);
     return 2;
   }
   const std::string mode = argv[1];
   if (mode == "merge") return run_merge(argv[2], argv[3]);
   if (mode == "eval") return run_eval(argv[2], argv[3]);
+  if (mode == "store") return run_store(argv[2], argv[3]);
   std::fprintf(stderr, "unknown mode %s\n", argv[1]);
   return 2;
 }

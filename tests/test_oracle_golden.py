@@ -211,3 +211,27 @@ def test_oracle_and_product_evaluator_match_reference_evaluator():
                            ggnn.DistanceMeasure(measure)).evaluate_results(torch.from_numpy(res))
         mine = np.array([e.c1, e.c1_dup, e.c_k_query, e.c_k_query_dup, e.r_k_query, e.r_k_query_dup], np.float64)
         assert np.allclose(mine, want.astype(np.float64), rtol=0, atol=1e-6), (case, mine, want)
+
+
+def test_vecs_io_matches_reference_dataset_store_and_load(tmp_path):
+    """fvecs / bvecs / ivecs (SURVEY 8f rank 3): tests/golden/ref_store.* were written by the reference's Dataset<T>::store
+    (src/ggnn/base/dataset.cu:215-226); our store() must produce the same bytes, our load() the same rows -- whole file
+    and the (from, num) ranges the reference's own load returned (dataset.cu:118-213) -- and asking for more rows than
+    the file holds must fail like the reference's CHECK_EQ"""
+    import os
+    import torch
+    import ggnn_b200 as ggnn
+    G, z = _host_golden()
+    cls = {"fvecs": ggnn.FloatDataset, "bvecs": ggnn.UCharDataset, "ivecs": ggnn.IntDataset}
+    for i, case in enumerate(G.IO_CASES):
+        _, dt, ext, N, D, (lo, num) = case
+        data = G.io_inputs(case, 300 + i)
+        ref_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_store.{ext}")
+        mine = str(tmp_path / f"mine.{ext}")
+        cls[ext](torch.from_numpy(data)).store(mine)
+        assert open(mine, "rb").read() == open(ref_file, "rb").read()
+        assert np.array_equal(cls[ext].load(ref_file).tensor.numpy(), data)
+        part = cls[ext].load(ref_file, lo, num).tensor.numpy()
+        assert np.array_equal(part, z[f"io{i}_loaded"]) and np.array_equal(part, data[lo:lo + num])
+        with pytest.raises(ValueError):
+            cls[ext].load(ref_file, 1, N)  # fewer vectors than requested

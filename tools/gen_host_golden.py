@@ -73,6 +73,16 @@ def eval_inputs(case, seed):
     return base, query, gt, res
 
 
+# vecs IO (src/ggnn/base/dataset.cu:118-226): type code of ref_host_check, numpy dtype, file extension, N, D, (from, num) of the range read
+IO_CASES = [(0, np.float32, "fvecs", 7, 5, (2, 3)), (1, np.uint8, "bvecs", 9, 16, (0, 9)), (2, np.int32, "ivecs", 6, 3, (5, 1))]
+
+
+def io_inputs(case, seed):
+    _, dt, _, N, D, _ = case
+    rng = np.random.default_rng(seed)
+    return (rng.random((N, D), dtype=np.float32) if dt == np.float32 else rng.integers(0, 200, (N, D)).astype(dt))
+
+
 def run_driver(mode, payload):
     with tempfile.TemporaryDirectory() as tmp:
         fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
@@ -104,6 +114,21 @@ def main():
         out[f"eval{i}_top1_end"] = raw[24:24 + 4 * Nq].view(np.uint32).copy()
         out[f"eval{i}_topk_end"] = raw[24 + 4 * Nq:].view(np.uint32).copy()
         print(case, out[f"eval{i}_values"], "dups:", int((out[f"eval{i}_top1_end"] > 1).sum()), int((out[f"eval{i}_topk_end"] > case[4]).sum()))
+    # vecs files: written by the reference's Dataset<T>::store (committed next to the npz), ranges read back by its load
+    for i, case in enumerate(IO_CASES):
+        code, dt, ext, N, D, (lo, num) = case
+        data = io_inputs(case, 300 + i)
+        path = os.path.join(ROOT, "tests", "golden", f"ref_store.{ext}")
+        with tempfile.TemporaryDirectory() as tmp:
+            fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+            with open(fin, "wb") as f:
+                f.write(np.array([code, N, D], np.uint32).tobytes() + data.tobytes())
+            subprocess.run([DRIVER, "store", fin, path], check=True)
+            subprocess.run([DRIVER, "load", path, str(lo), str(num), fout], check=True)
+            raw = np.fromfile(fout, dtype=np.uint8)
+        n, d, esz = raw[:12].view(np.uint32)
+        assert (n, d, esz) == (num, D, np.dtype(dt).itemsize), (n, d, esz)
+        out[f"io{i}_loaded"] = raw[12:].view(dt).reshape(n, d).copy()
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
