@@ -713,7 +713,8 @@ def run_extras(a, idx, base, query, gt, dev, build_s, build_warm_s, build_passes
                                         "k10_ms": ms_bf8, "k100_ms": ms_bf8_100,
                                         "k10_useful_tops": 2.0 * Nq * a.n_base * a.dim / (ms_bf8 * 1e-3) / 1e12,
                                         "ids_identical_to_fp32_bf_query": bool(torch.equal(b8i, gt)),
-                                        "ids_crc32_k10": _crc(b8i), "ids_crc32_k100": _crc(b8i100)}
+                                        "ids_crc32_k10": _crc(b8i), "ids_crc32_k100": _crc(b8i100),
+                                        "tensor_pipe": load_profile_note("bf_i8")}
             except Exception as e:  # noqa: BLE001
                 ex["bf_query_uint8"] = {"error": repr(e)[-300:]}
             del g8
